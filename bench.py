@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the SPGG lattice step (BASELINE.json metric: site-updates/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A bench "step" is one chunk of ``--inner`` lattice iterations (default 100) of the whole
+L x L lattice through ``spgg_step`` (statistics on).  N=1 runs BASELINE config 4
+(L=4096, reputation state, M=1, r=3, kappa=1, w_P=0.95, fp32 throughput mode).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_SITE_FP32 = 34.25   # Q 16r+16w, R int8 1r+1w, S bit 1/8r+1/8w
+C4 = dict(r=3.0, c=1, cost=1, alpha=0.8, gamma=0.9, epsilon=0.5, epsilon_decay=0.99,
+          epsilon_min=0.01, influence_factor=1.0, use_second_order=False, lambda_epsilon=0.01,
+          delta_R_C=1, delta_R_D=1, R_min=-10, R_max=10, reward_weight_payoff=0.95,
+          rep_gain_C=1.0, state_representation="reputation")
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_numpy(L, iters, seed=0):
+    """The reference's NumPy path restated (oracle/spgg_numpy.py, pinned bit-exact to the
+    reference), timed on this host.  Returns site-updates/s."""
+    from oracle import spgg_numpy
+    p = dict(C4, L=L, iterations=iters)
+    rs = np.random.RandomState(seed)
+    Q = rs.uniform(-0.01, 0.01, (L, L, 2, 2))
+    S = rs.randint(0, 2, (L, L)).astype(np.int64)
+    R = np.zeros((L, L))
+    eps = p["epsilon"]
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        u = rs.rand(L, L)
+        b = rs.randint(0, 2, (L, L))
+        S, R, Q, _st = spgg_numpy.qlearning_step(S, R, Q, eps, u, b, p)
+        eps = max(eps * p["epsilon_decay"], p["epsilon_min"])
+    dt = time.perf_counter() - t0
+    return L * L * iters / dt, dt
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference is
+    pure Python and cannot travel to the GPU box (and may not be copied), so this is its
+    NumPy restatement (oracle port, bit-exact to it), single process like the reference's
+    own loop (its NumPy ops are single-threaded)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    # bounded sample: one iteration of an Ls x Ls lattice per step, ~100 M site-updates in all
+    budget_sites = 9.0e7
+    Ls = int(min(4096, max(128, (budget_sites / max(1, steps + warm)) ** 0.5)))
+    Ls -= Ls % 32
+    from oracle import spgg_numpy
+    p = dict(C4, L=Ls)
+    rs = np.random.RandomState(0)
+    Q = rs.uniform(-0.01, 0.01, (Ls, Ls, 2, 2))
+    S = rs.randint(0, 2, (Ls, Ls)).astype(np.int64)
+    R = np.zeros((Ls, Ls))
+    eps = p["epsilon"]
+    t_timed = 0.0
+    for it in range(warm + steps):
+        u = rs.rand(Ls, Ls)
+        b = rs.randint(0, 2, (Ls, Ls))
+        t0 = time.perf_counter()
+        S, R, Q, _ = spgg_numpy.qlearning_step(S, R, Q, eps, u, b, p)
+        dt = time.perf_counter() - t0
+        eps = max(eps * p["epsilon_decay"], p["epsilon_min"])
+        if it >= warm:
+            t_timed += dt
+    value = Ls * Ls * steps / t_timed
+    sample = f"{steps} iterations of an L={Ls} lattice (same physics as the L=4096 workload)"
+    line = {
+        "impl": "reference", "metric": "site-updates/s", "value": value, "unit": "site-updates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * t_timed / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 physics: reputation state, M=1, r=3, kappa=1, w_P=0.95 "
+                               f"(reference NumPy path restated; sample lattice L={Ls})"},
+        "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": 1, "kind": "port",
+                         "sample": sample, "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--inner", type=int, default=100, help="lattice iterations per bench step")
+    ap.add_argument("--L", type=int, default=None)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-L", type=int, default=4096)
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import spgg_b200
+    from spgg_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from spgg_b200 import strips
+        return strips.bench_main(args, rank, local_rank, world)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dev = 0
+    torch.cuda.set_device(dev)
+    L = args.L or 4096
+    K, W, inner = args.steps, args.warmup, args.inner
+    p = dict(C4, L=L)
+    n_sites = L * L
+    peak, peak_src = measured_peak_gbs()
+
+    # host state in pinned memory (reference layouts: uint8 S, f64 R, f64 Q)
+    rs = np.random.RandomState(0)
+    S_h = torch.empty((L, L), dtype=torch.uint8).pin_memory()
+    R_h = torch.zeros((L, L), dtype=torch.float64).pin_memory()
+    Q_h = torch.empty((L, L, 2, 2), dtype=torch.float64).pin_memory()
+    S_h.numpy()[...] = rs.randint(0, 2, (L, L))
+    Q_h.numpy()[...] = rs.uniform(-0.01, 0.01, (L, L, 2, 2))
+    S_out = torch.empty_like(S_h).pin_memory()
+    R_out = torch.empty_like(R_h).pin_memory()
+    Q_out = torch.empty_like(Q_h).pin_memory()
+
+    eng = spgg_b200.Engine(p, seeds=2024, precision="fp32", device=dev)
+    lib, h = eng.lib, eng._h
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def upload():
+        _lib.check(lib.spgg_set_state(h, 0, S_h.data_ptr(), R_h.data_ptr(), Q_h.data_ptr()))
+
+    # ---------------- warm-up
+    upload()
+    for _ in range(W):
+        eng.step(inner, stream)
+    eng.sync()
+
+    # ---------------- device-resident timed region (value)
+    upload()
+    l0 = eng.status().kernel_launches
+    sampler = ClockSampler(dev)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        _lib.check(lib.spgg_step(h, inner, stream))
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    eng.sync()
+    launches = eng.status().kernel_launches - l0
+    value = n_sites * inner * K / (ms * 1e-3)
+
+    # ---------------- end to end through the public API with host buffers
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    upload()
+    d2h_stats = 0
+    for _ in range(K):
+        eng.step(inner, stream)
+        rows = eng.stats()
+        d2h_stats += rows.nbytes
+    _lib.check(lib.spgg_get_state(h, 0, S_out.data_ptr(), R_out.data_ptr(), Q_out.data_ptr()))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    state_bytes = S_h.numel() + R_h.numel() * 8 + Q_h.numel() * 8
+    e2e_value = n_sites * inner * K / t_e2e
+
+    # ---------------- per-kernel timing (roofline of the dominant kernel, k_step)
+    n_probe = min(200, inner * K)
+    _lib.check(lib.spgg_begin_steps(h, n_probe, stream))
+    _lib.check(lib.spgg_phase_kernel(h, 0, 1, stream))
+    evs = []
+    for s in range(1, n_probe + 1):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        _lib.check(lib.spgg_phase_gmax(h, stream))
+        b.record()
+        _lib.check(lib.spgg_phase_kernel(h, 1, 1 if s < n_probe else 0, stream))
+        c.record()
+        evs.append((a, b, c))
+    _lib.check(lib.spgg_end_steps(h, stream))
+    torch.cuda.synchronize()
+    eng.sync()
+    t_gmax = float(np.mean([a.elapsed_time(b) for a, b, c in evs[:-1]])) * 1e-3
+    t_step = float(np.mean([b.elapsed_time(c) for a, b, c in evs[:-1]])) * 1e-3
+    achieved = BYTES_PER_SITE_FP32 * n_sites / t_step / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel": "k_step<ModeF32I8,1,rep,philox>",
+                "kernel_us": t_step * 1e6, "gmax_kernel_us": t_gmax * 1e6,
+                "algorithmic_bytes_per_site": BYTES_PER_SITE_FP32, "peak_source": peak_src,
+                "whole_step_frac": BYTES_PER_SITE_FP32 * value / 1e9 / peak}
+
+    # ---------------- CPU baseline beside it (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt = cpu_baseline_numpy(args.cpu_L, 1)
+        cpu = {"value": v, "unit": "site-updates/s", "cores": 1, "kind": "port",
+               "sample": f"1 iteration of the L={args.cpu_L} lattice with the NumPy restatement of the "
+                         f"reference path ({dt:.1f} s)", "host_cpus": os.cpu_count()}
+
+    line = {
+        "metric": "site-updates/s", "value": value, "unit": "site-updates/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C4: single lattice L={L}, reputation state, M=1, r=3, kappa=1, "
+                               f"w_P=0.95, Q-learning; {inner} iterations per bench step, "
+                               "statistics on, Philox draws",
+                   "L": L, "iterations_per_step": inner, "precision": "fp32 Q (float4) + int8 R + bit S",
+                   "l2": f"state {state_bytes_dev(L) / 1e6:.0f} MB per pass > 126 MB L2 (no flush needed)",
+                   "e2e_def": "SPGG C-ABI with host buffers: set_state (H2D of uint8 S, f64 R, f64 Q) + "
+                              "K chunks with the stat rows read back each chunk + get_state (D2H), "
+                              "all inside the timed region"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "site-updates/s",
+                "h2d_bytes_per_step": state_bytes / K, "d2h_bytes_per_step": (state_bytes + d2h_stats) / K,
+                "seconds": t_e2e},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def state_bytes_dev(L):
+    return L * L * (16 + 1 + 1 + 0.125)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+/* libspgg_b200 - C ABI of the B200-native SPGG lattice step.
+ *
+ * The reference (jac0626/Neighbor-Aware-Reinforcement-Learning-...) is pure
+ * Python/NumPy and has no FFI of its own; the only boundary of the hot path is
+ * the Python class `SPGG` (reference src/model/spgg.py:39-637).  This header
+ * is what a Python (ctypes) binding of that class binds instead of the NumPy
+ * loop body; every entry point names the reference lines it replaces
+ * (paths relative to the reference root).  Plain pointers and sizes only.
+ *
+ * Conventions: host buffers are caller-owned; device memory is owned by the
+ * handle; functions return 0 on success and a negative code on failure, with
+ * a message available from spgg_last_error() (thread-local).  One host thread
+ * per handle.  All GPU work is enqueued on the stream passed to spgg_step().
+ * CUDA is initialised lazily by the first spgg_create() of a process (fork
+ * safe until then, reference src/experiments/runner.py:142 forks workers).
+ */
+#ifndef SPGG_B200_H
+#define SPGG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPGG_ABI_VERSION 1
+
+/* error codes */
+#define SPGG_OK 0
+#define SPGG_E_INVALID (-1)   /* bad argument (Python side raises ValueError)  */
+#define SPGG_E_CUDA (-2)      /* CUDA runtime failure                          */
+#define SPGG_E_STATE (-3)     /* call not valid in the handle's current state  */
+#define SPGG_E_UNSUPPORTED (-4)
+
+/* precision / arithmetic */
+#define SPGG_PREC_FP32 0 /* throughput mode: fp32 float4 Q, int8|fp32 R, exact-count reward table */
+#define SPGG_PREC_FP64 1 /* parity mode: fp64 Q and R, reference operation order, no FMA          */
+
+/* state_representation (spgg.py:289-310) */
+#define SPGG_STATE_REPUTATION 0
+#define SPGG_STATE_ACTION 1
+
+/* algorithm (algorithms.py:344-383) */
+#define SPGG_ALGO_QLEARNING 0
+
+/* reputation storage in fp32 mode */
+#define SPGG_RSTORE_AUTO 0 /* int8 when rep_gain_C, delta_R_D, R_min, R_max are multiples of 2^-k that fit */
+#define SPGG_RSTORE_INT8 1
+#define SPGG_RSTORE_FP32 2
+
+/* Statistics row: one row of SPGG_NSTAT doubles per iteration and replica.
+ * Sums, not means; the host divides (spgg.py:381-394, 419-426, 512-592). */
+#define SPGG_NSTAT 40
+enum spgg_stat {
+  SPGG_ST_NC_OLD = 0,      /* #cooperators in S before the action          spgg.py:383 */
+  SPGG_ST_N_CD = 1,        /* C->D switches                                spgg.py:419 */
+  SPGG_ST_N_DC = 2,        /* D->C switches                                spgg.py:420 */
+  SPGG_ST_NC_NEW = 3,      /* #sites whose action is C                                 */
+  SPGG_ST_SUM_P = 4,       /* sum P                                        spgg.py:388 */
+  SPGG_ST_SUM_P_C = 5,     /* sum P over previous cooperators              spgg.py:389 */
+  SPGG_ST_SUM_P_D = 6,     /* sum P over previous defectors                spgg.py:390 */
+  SPGG_ST_SUM_WP_P = 7,    /* sum w_P*P                                    spgg.py:425 */
+  SPGG_ST_SUM_REW_C = 8,   /* sum reward over a==C                         spgg.py:542 */
+  SPGG_ST_SUM_REW_D = 9,   /* sum reward over a==D                         spgg.py:543 */
+  SPGG_ST_SUM_RATIO = 10,  /* sum_{a==C} |w_R*.5|/(|rew|+1e-9)*100         spgg.py:529-536 */
+  SPGG_ST_GROUP0 = 11,     /* 11..16: #groups with k=0..5 defectors (new S) spgg.py:586-592 */
+  SPGG_ST_SUM_R = 17,      /* sum of R of the state the row index names (row j: R_j) spgg.py:394 */
+  SPGG_ST_SUM_Q = 18,      /* 18..21: sum Q[:,:,s,a] after both updates    spgg.py:562-565 */
+  SPGG_ST_SUM_Q_C = 22,    /* 22..25: same, previous cooperators           spgg.py:568-583 */
+  SPGG_ST_SUM_Q_D = 26,    /* 26..29: same, previous defectors                         */
+  SPGG_ST_SUM_NI = 30,     /* sum neighbour-influence percent              spgg.py:512 */
+  SPGG_ST_N_BEST_POS = 31, /* #sites with max_diff>0                       spgg.py:521 */
+  SPGG_ST_N_BEST_2ND = 32, /* ... whose best neighbour is second order     spgg.py:520 */
+  SPGG_ST_GMAX = 33        /* lattice-global max|diff|                     spgg.py:488 */
+};
+
+/* Replaces the keyword arguments of SPGG.__init__ that influence the
+ * dynamics (spgg.py:50-56); K, population_type, delta_R_C and
+ * num_of_strategies are never read by the loop and are not part of the ABI. */
+typedef struct spgg_params {
+  int32_t L;          /* lattice side (columns; rows too unless a strip)             */
+  int32_t rows;       /* rows owned by this handle: L, or the strip height           */
+  int32_t row0;       /* global index of the first owned row (strips)                */
+  int32_t M;          /* 1 or 2: use_second_order                                    */
+  int32_t state_mode; /* SPGG_STATE_*                                                */
+  int32_t precision;  /* SPGG_PREC_*                                                 */
+  int32_t algorithm;  /* SPGG_ALGO_*                                                 */
+  int32_t r_storage;  /* SPGG_RSTORE_*                                               */
+  double r, c, cost;
+  double alpha, gamma;
+  double epsilon, epsilon_decay, epsilon_min;
+  double kappa;       /* influence_factor                                            */
+  double lambda_eps;
+  double rep_gain_C, delta_R_D, R_min, R_max;
+  double wP;          /* reward_weight_payoff                                        */
+  uint64_t seed;      /* Philox key                                                  */
+} spgg_params_t;
+
+typedef struct spgg_status {
+  int64_t iteration;   /* completed iterations (state index t: S_t, R_t, Q_t)        */
+  int64_t stopped_at;  /* -1, or the t whose S_t is uniform: iteration t+1 breaks (spgg.py:405) */
+  double epsilon;      /* epsilon after `iteration` decays (algorithms.py:40-42)     */
+  int32_t n_replicas;
+  int32_t r_is_int8;
+  int64_t kernel_launches; /* kernels launched by this handle so far                 */
+} spgg_status_t;
+
+typedef struct spgg_handle spgg_t;
+
+/* SPGG.__init__ (spgg.py:50-156) without the random initial state.  n_replicas
+ * independent lattices share L, rows, M, state_mode, precision; everything
+ * else may differ per replica (params is an array of n_replicas entries).
+ * Replaces one multiprocessing worker per parameter tuple (runner.py:117-156). */
+int spgg_create(const spgg_params_t *params, int n_replicas, int device, spgg_t **out);
+void spgg_destroy(spgg_t *h);
+
+/* Upload q_table (rows*L*2*2 doubles, layout of spgg.py:121), R (rows*L
+ * doubles, spgg.py:129) and _Sn (rows*L bytes, 0=C 1=D, spgg.py:162) of one
+ * replica.  Resets that replica's iteration counter and epsilon. */
+int spgg_set_state(spgg_t *h, int replica, const uint8_t *S, const double *R, const double *Q);
+int spgg_get_state(spgg_t *h, int replica, uint8_t *S, double *R, double *Q);
+
+/* Same distributions as the reference ctor (Q ~ U(-0.01,0.01) spgg.py:121, R = 0
+ * spgg.py:129, S ~ Bernoulli(1/2) spgg.py:162) generated on the device from Philox
+ * keyed by `seed`; for lattices too large to stage through host memory. */
+int spgg_init_random(spgg_t *h, int replica, uint64_t seed);
+
+/* Replay mode: the draw arrays the reference would consume in the next
+ * n_steps iterations (algorithms.py:105 `rand(L,L)` and :108
+ * `randint(0,2,(L,L))`), each n_steps*rows*L.  Single replica only.  Consumed
+ * by the following spgg_step calls; Philox is used once they run out. */
+int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const uint8_t *b);
+
+/* Run n_steps iterations of the loop body spgg.py:368-592 for all replicas
+ * (asynchronous on `cuda_stream`, a cudaStream_t or NULL). */
+int spgg_step(spgg_t *h, int n_steps, void *cuda_stream);
+int spgg_sync(spgg_t *h);
+
+/* Statistic rows of the last spgg_step call: rows [first, first+n) relative
+ * to the iteration index at the start of that call (row 0 = starting state:
+ * only SPGG_ST_SUM_R is meaningful; row k = iteration start+k). */
+int spgg_get_stats(spgg_t *h, int replica, int first, int n, double *rows_out);
+int spgg_query(spgg_t *h, int replica, spgg_status_t *out);
+
+/* Strip decomposition (multi-GPU): boundary rows <-> ghost rows.  pack copies
+ * the rows a neighbour needs into two contiguous device buffers of
+ * spgg_halo_bytes() each (up = towards row0-1, down = towards row0+rows);
+ * unpack fills this strip's ghost rows from the neighbours' buffers. */
+int64_t spgg_halo_bytes(spgg_t *h);
+int spgg_halo_pack(spgg_t *h, void *dev_to_up, void *dev_to_down, void *cuda_stream);
+int spgg_halo_unpack(spgg_t *h, const void *dev_from_up, const void *dev_from_down,
+                     void *cuda_stream);
+/* Phase-split stepping for strips: select (K with update of iteration j when
+ * j>0), then halo exchange, then gmax partial, then all-reduce(max) of the
+ * value at spgg_gmax_device_ptr(), repeat. */
+int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *cuda_stream);
+int spgg_phase_gmax(spgg_t *h, void *cuda_stream);
+void *spgg_gmax_device_ptr(spgg_t *h);
+int spgg_begin_steps(spgg_t *h, int n_steps, void *cuda_stream);
+int spgg_end_steps(spgg_t *h, void *cuda_stream);
+
+const char *spgg_last_error(void);
+int spgg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPGG_B200_H */

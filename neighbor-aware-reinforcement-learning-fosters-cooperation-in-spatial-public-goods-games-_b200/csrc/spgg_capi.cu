@@ -1,0 +1,684 @@
+// C ABI of libspgg_b200 (include/spgg.h): handle, device memory, launch sequencing.
+// The arithmetic lives in spgg_kernels.cuh.  No CPU fallback: every entry point that
+// computes needs a CUDA device and fails with SPGG_E_CUDA otherwise.
+#include "../../include/spgg.h"
+#include "spgg_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace spgg;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(SPGG_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+enum { MODE_F32_I8 = 0, MODE_F32_F = 1, MODE_F64 = 2 };
+
+struct spgg_handle {
+  int device = 0;
+  int n_rep = 1;
+  int mode = MODE_F32_I8;
+  int M = 1;
+  int action = 0;
+  std::vector<spgg_params_t> params;
+  std::vector<RepConst> rc_host;
+  Geom g{};
+  int threads = 256;
+  size_t smem_step = 0, smem_gmax = 0;
+  // device memory
+  RepConst *d_rc = nullptr;
+  void *d_Q = nullptr;
+  void *d_R[2] = {nullptr, nullptr};
+  void *d_code[2] = {nullptr, nullptr};
+  uint32_t *d_S[2] = {nullptr, nullptr};
+  int cur = 0;  // planes holding the state of iteration `iter`
+  void *d_gmax = nullptr;
+  double *d_stats = nullptr;
+  double *d_partials = nullptr;
+  unsigned *d_tickets = nullptr;
+  int *d_stop = nullptr;
+  double *d_eps = nullptr;
+  uint32_t *d_thr = nullptr;
+  int cap = 0;  // rows per replica of stats/gmax/eps tables
+  double *d_u = nullptr;
+  uint8_t *d_b = nullptr;
+  // staging scratch for set/get_state
+  uint8_t *d_sc_S = nullptr;
+  double *d_sc_R = nullptr, *d_sc_Q = nullptr;
+  unsigned long long *d_sc_info = nullptr;
+  std::vector<double> eps_host;
+  std::vector<uint32_t> thr_host;
+  long long replay_first = 0, replay_n = 0;  // draws cover iterations replay_first+1 .. replay_first+replay_n
+  // host bookkeeping
+  long long iter = 0;
+  std::vector<double> eps_cur;     // eps used at iteration iter+1
+  std::vector<long long> stop_at;  // -1 or the t with uniform S_t
+  long long launches = 0;
+  // pending asynchronous chunk
+  bool pending = false;
+  long long pend_t0 = 0;
+  int pend_n = 0, pend_cur0 = 0, pend_rel = 0;
+  cudaStream_t pend_stream = nullptr;
+  size_t elem_code() const { return mode == MODE_F64 ? 4 : 1; }
+  size_t elem_R() const { return mode == MODE_F64 ? 8 : (mode == MODE_F32_F ? 4 : 1); }
+  size_t elem_Q() const { return mode == MODE_F64 ? 8 : 4; }
+  size_t elem_val() const { return mode == MODE_F64 ? 8 : 4; }
+};
+
+// ---------------------------------------------------------------- constants
+static bool int8_quantum(const spgg_params_t &p, double *rq, int *gi, int *li, int *mn, int *mx) {
+  for (int k = 0; k <= 4; ++k) {
+    const double s = (double)(1 << k);
+    const double a = p.rep_gain_C * s, b = p.delta_R_D * s, c = p.R_min * s, d = p.R_max * s;
+    if (a == std::floor(a) && b == std::floor(b) && c == std::floor(c) && d == std::floor(d) &&
+        std::fabs(c) <= 127 && std::fabs(d) <= 127 && std::fabs(a) <= 127 && std::fabs(b) <= 127 &&
+        c - b >= -128 && d + a <= 127) {
+      *rq = 1.0 / s; *gi = (int)a; *li = (int)b; *mn = (int)c; *mx = (int)d;
+      return true;
+    }
+  }
+  return false;
+}
+
+static void build_repconst(const spgg_params_t &p, RepConst *rc) {
+  memset(rc, 0, sizeof(*rc));
+  rc->rc = p.r * p.c;
+  for (int n = 0; n < 6; ++n) rc->g[n] = rc->rc * (double)n / 5.0;  // spgg.py:256
+  rc->cost = p.cost;
+  rc->lo = p.r - 5.0;                // spgg.py:149
+  rc->span = 4.0 * p.r - rc->lo;     // spgg.py:148,377
+  rc->wP = p.wP;
+  rc->wR = 1.0 - p.wP;               // spgg.py:108
+  rc->alpha = p.alpha; rc->gamma = p.gamma; rc->kappa = p.kappa; rc->leps = p.lambda_eps;
+  rc->gainC = p.rep_gain_C; rc->lossD = p.delta_R_D; rc->rmin = p.R_min; rc->rmax = p.R_max;
+  rc->alpha_f = (float)p.alpha; rc->gamma_f = (float)p.gamma; rc->kappa_f = (float)p.kappa;
+  rc->leps_f = (float)p.lambda_eps;
+  rc->gainC_f = (float)p.rep_gain_C; rc->lossD_f = (float)p.delta_R_D;
+  rc->rmin_f = (float)p.R_min; rc->rmax_f = (float)p.R_max;
+  rc->rq = 1.0;
+  int8_quantum(p, &rc->rq, &rc->gain_i, &rc->loss_i, &rc->rmin_i, &rc->rmax_i);
+  rc->seed_lo = (uint32_t)p.seed;
+  rc->seed_hi = (uint32_t)(p.seed >> 32);
+  rc->has_ratio = (rc->wR != 0.0);
+  for (int code = 0; code < 128; ++code) {
+    const int sn = code >> 2, C = (code >> 1) & 1, coop = code & 1;
+    const double tot = rc->rc * (double)sn / 5.0 - (C ? 5.0 * p.cost : 0.0);
+    const double P = (tot - rc->lo) / rc->span;
+    const double rew = rc->wP * P + rc->wR * (coop ? 0.5 : 0.0);
+    rc->rewtab[code] = (float)rew;
+    rc->ratiotab[code] =
+        coop ? (float)(std::fabs(rc->wR * 0.5) / (std::fabs(rew) + 1e-9) * 100.0) : 0.0f;
+  }
+}
+
+// ---------------------------------------------------------------- dispatch
+typedef void (*step_fn_t)(KArgs);
+typedef void (*gmax_fn_t)(GArgs);
+
+template <class Md, int M>
+static step_fn_t pick_step2(int action, int replay) {
+  if (action) return replay ? k_step<Md, M, true, true> : k_step<Md, M, true, false>;
+  return replay ? k_step<Md, M, false, true> : k_step<Md, M, false, false>;
+}
+template <class Md>
+static step_fn_t pick_step1(int M, int action, int replay) {
+  return M == 2 ? pick_step2<Md, 2>(action, replay) : pick_step2<Md, 1>(action, replay);
+}
+static step_fn_t pick_step(int mode, int M, int action, int replay) {
+  switch (mode) {
+    case MODE_F32_I8: return pick_step1<ModeF32I8>(M, action, replay);
+    case MODE_F32_F: return pick_step1<ModeF32F>(M, action, replay);
+    default: return pick_step1<ModeF64>(M, action, replay);
+  }
+}
+static gmax_fn_t pick_gmax(int mode, int M) {
+  switch (mode) {
+    case MODE_F32_I8: return M == 2 ? k_gmax<ModeF32I8, 2> : k_gmax<ModeF32I8, 1>;
+    case MODE_F32_F: return M == 2 ? k_gmax<ModeF32F, 2> : k_gmax<ModeF32F, 1>;
+    default: return M == 2 ? k_gmax<ModeF64, 2> : k_gmax<ModeF64, 1>;
+  }
+}
+static size_t step_smem(int mode, int TR) {
+  switch (mode) {
+    case MODE_F32_I8: return SmemLayout<ModeF32I8>(TR).total;
+    case MODE_F32_F: return SmemLayout<ModeF32F>(TR).total;
+    default: return SmemLayout<ModeF64>(TR).total;
+  }
+}
+
+// ---------------------------------------------------------------- lifetime
+extern "C" int spgg_abi_version(void) { return SPGG_ABI_VERSION; }
+extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
+
+static int free_all(spgg_handle *h) {
+  cudaFree(h->d_rc); cudaFree(h->d_Q);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->d_R[i]); cudaFree(h->d_code[i]); cudaFree(h->d_S[i]); }
+  cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_partials); cudaFree(h->d_tickets);
+  cudaFree(h->d_stop); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_u); cudaFree(h->d_b);
+  cudaFree(h->d_sc_S); cudaFree(h->d_sc_R); cudaFree(h->d_sc_Q); cudaFree(h->d_sc_info);
+  return 0;
+}
+
+extern "C" void spgg_destroy(spgg_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_all(h);
+  delete h;
+}
+
+extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int device, spgg_t **out) {
+  if (!params || !out || n_replicas < 1) return fail(SPGG_E_INVALID, "spgg_create: null argument or n_replicas < 1");
+  const spgg_params_t &p0 = params[0];
+  if (p0.L < 4) return fail(SPGG_E_INVALID, "L must be >= 4 (got %d)", p0.L);
+  if (p0.rows < 2 * GH || p0.rows > p0.L)
+    return fail(SPGG_E_INVALID, "rows must be in [%d, L] (got %d)", 2 * GH, p0.rows);
+  if (p0.M != 1 && p0.M != 2) return fail(SPGG_E_INVALID, "M must be 1 or 2 (got %d)", p0.M);
+  if (p0.state_mode != SPGG_STATE_REPUTATION && p0.state_mode != SPGG_STATE_ACTION)
+    return fail(SPGG_E_INVALID, "Unknown state_representation code %d", p0.state_mode);
+  if (p0.precision != SPGG_PREC_FP32 && p0.precision != SPGG_PREC_FP64)
+    return fail(SPGG_E_INVALID, "unknown precision %d", p0.precision);
+  if (p0.algorithm != SPGG_ALGO_QLEARNING)
+    return fail(SPGG_E_UNSUPPORTED, "algorithm code %d is not built into the fused kernel", p0.algorithm);
+  if (p0.row0 < 0 || p0.row0 + p0.rows > p0.L) return fail(SPGG_E_INVALID, "row0/rows outside the lattice");
+  for (int r = 1; r < n_replicas; ++r) {
+    const spgg_params_t &p = params[r];
+    if (p.L != p0.L || p.rows != p0.rows || p.row0 != p0.row0 || p.M != p0.M ||
+        p.state_mode != p0.state_mode || p.precision != p0.precision ||
+        p.algorithm != p0.algorithm || p.r_storage != p0.r_storage)
+      return fail(SPGG_E_INVALID, "replica %d differs in a batch-invariant field (L, rows, M, state, precision)", r);
+  }
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SPGG_E_CUDA, "device %d not available (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+
+  spgg_handle *h = new spgg_handle();
+  h->device = device;
+  h->n_rep = n_replicas;
+  h->params.assign(params, params + n_replicas);
+  h->M = p0.M;
+  h->action = p0.state_mode == SPGG_STATE_ACTION;
+  h->rc_host.resize(n_replicas);
+  bool all_i8 = true;
+  for (int r = 0; r < n_replicas; ++r) {
+    build_repconst(params[r], &h->rc_host[r]);
+    double rq; int a, b, c, d;
+    all_i8 = all_i8 && int8_quantum(params[r], &rq, &a, &b, &c, &d);
+  }
+  if (p0.precision == SPGG_PREC_FP64) h->mode = MODE_F64;
+  else if (p0.r_storage == SPGG_RSTORE_FP32) h->mode = MODE_F32_F;
+  else if (p0.r_storage == SPGG_RSTORE_INT8) {
+    if (!all_i8) { delete h; return fail(SPGG_E_INVALID, "reputation parameters are not representable in int8 units"); }
+    h->mode = MODE_F32_I8;
+  } else h->mode = all_i8 ? MODE_F32_I8 : MODE_F32_F;
+
+  Geom &g = h->g;
+  g.L = p0.L; g.rows = p0.rows; g.row0 = p0.row0; g.wrap_rows = (p0.rows == p0.L);
+  g.pitchB = (p0.L + 15) / 16 * 16;
+  g.pitchW = ((p0.L + 31) / 32 + 3) / 4 * 4;
+  g.TR = g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4);
+  h->threads = 32 * std::min(8, g.TR);
+  g.n_tx = (g.L + TC - 1) / TC;
+  g.n_ty = (g.rows + g.TR - 1) / g.TR;
+  g.n_rep = n_replicas;
+  g.plane_stride = (long long)(g.rows + 2 * GH) * g.pitchB;
+  g.bits_stride = (long long)(g.rows + 2 * GH) * g.pitchW;
+  g.site_stride = (long long)g.rows * g.L;
+  h->smem_step = step_smem(h->mode, g.TR);
+  h->smem_gmax = (h->elem_val() * (size_t)(g.TR + 2 * HR) * SMW + 15) / 16 * 16 + 512;
+
+  // opt in to the shared memory each instantiation needs and size the persistent grid
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  int occ = 1;
+  for (int replay = 0; replay < 2; ++replay) {
+    step_fn_t f = pick_step(h->mode, h->M, h->action, replay);
+    CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
+    if (!replay)
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, h->threads, h->smem_step));
+  }
+  CUDA_TRY(cudaFuncSetAttribute(pick_gmax(h->mode, h->M), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)h->smem_gmax));
+  if (occ < 1) { delete h; return fail(SPGG_E_CUDA, "kernel does not fit on an SM (smem %zu)", h->smem_step); }
+  const long long n_tiles = (long long)g.n_tx * g.n_ty;
+  long long per_rep = std::max<long long>(1, ((long long)prop.multiProcessorCount * occ) / n_replicas);
+  g.ctas_per_rep = (int)std::min<long long>(n_tiles, per_rep);
+
+  const size_t nQ = (size_t)n_replicas * g.site_stride * 4 * h->elem_Q();
+  const size_t nR = (size_t)n_replicas * g.plane_stride * h->elem_R();
+  const size_t nC = (size_t)n_replicas * g.plane_stride * h->elem_code();
+  const size_t nS = (size_t)n_replicas * g.bits_stride * 4;
+#define ALLOC(ptr, bytes)                                                                   \
+  do {                                                                                      \
+    cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                  \
+    if (e_ != cudaSuccess) {                                                                \
+      free_all(h); delete h;                                                                \
+      return fail(SPGG_E_CUDA, "cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+    }                                                                                       \
+    cudaMemset((ptr), 0, (bytes));                                                          \
+  } while (0)
+  ALLOC(h->d_rc, sizeof(RepConst) * n_replicas);
+  ALLOC(h->d_Q, nQ);
+  for (int i = 0; i < 2; ++i) { ALLOC(h->d_R[i], nR); ALLOC(h->d_code[i], nC); ALLOC(h->d_S[i], nS); }
+  ALLOC(h->d_partials, sizeof(double) * (size_t)n_replicas * g.ctas_per_rep * NSTAT);
+  ALLOC(h->d_tickets, sizeof(unsigned) * n_replicas);
+  ALLOC(h->d_stop, sizeof(int) * n_replicas);
+#undef ALLOC
+  CUDA_TRY(cudaMemcpy(h->d_rc, h->rc_host.data(), sizeof(RepConst) * n_replicas, cudaMemcpyHostToDevice));
+  std::vector<int> neg(n_replicas, -1);
+  CUDA_TRY(cudaMemcpy(h->d_stop, neg.data(), sizeof(int) * n_replicas, cudaMemcpyHostToDevice));
+  h->eps_cur.resize(n_replicas);
+  for (int r = 0; r < n_replicas; ++r) h->eps_cur[r] = params[r].epsilon;
+  h->stop_at.assign(n_replicas, -1);
+  *out = h;
+  return SPGG_OK;
+}
+
+// ---------------------------------------------------------------- pending chunk
+static int finish_pending(spgg_handle *h) {
+  if (!h->pending) return SPGG_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->pend_stream));
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> stop(h->n_rep);
+  CUDA_TRY(cudaMemcpy(stop.data(), h->d_stop, sizeof(int) * h->n_rep, cudaMemcpyDeviceToHost));
+  // Replicas stop independently; plane parity is shared, so a stopped replica's planes are
+  // copied forward to the parity the running replicas ended on (single-replica: adjust cur).
+  const long long t_end = h->pend_t0 + h->pend_rel;
+  for (int r = 0; r < h->n_rep; ++r) {
+    h->stop_at[r] = stop[r];
+    const long long done = (stop[r] >= 0 && stop[r] < t_end) ? (long long)stop[r] : t_end;
+    double e = h->eps_cur[r];
+    for (long long t = h->pend_t0; t < done; ++t)
+      e = std::max(e * h->params[r].epsilon_decay, h->params[r].epsilon_min);  // algorithms.py:42
+    h->eps_cur[r] = e;
+  }
+  if (h->n_rep == 1 && stop[0] >= 0 && stop[0] < t_end) {
+    h->cur = h->pend_cur0 ^ (int)((stop[0] - h->pend_t0) & 1);
+    h->iter = stop[0];
+  } else {
+    if (h->n_rep > 1) {
+      for (int r = 0; r < h->n_rep; ++r) {
+        if (stop[r] >= 0 && stop[r] < t_end) {
+          const int src = h->pend_cur0 ^ (int)((stop[r] - h->pend_t0) & 1);
+          if (src != h->cur) {
+            const Geom &g = h->g;
+            CUDA_TRY(cudaMemcpy((char *)h->d_R[h->cur] + (size_t)r * g.plane_stride * h->elem_R(),
+                                (char *)h->d_R[src] + (size_t)r * g.plane_stride * h->elem_R(),
+                                (size_t)g.plane_stride * h->elem_R(), cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy(h->d_S[h->cur] + (size_t)r * g.bits_stride,
+                                h->d_S[src] + (size_t)r * g.bits_stride,
+                                (size_t)g.bits_stride * 4, cudaMemcpyDeviceToDevice));
+          }
+        }
+      }
+    }
+    h->iter = t_end;
+  }
+  h->pending = false;
+  return SPGG_OK;
+}
+
+extern "C" int spgg_sync(spgg_t *h) {
+  if (!h) return fail(SPGG_E_INVALID, "null handle");
+  return finish_pending(h);
+}
+
+// ---------------------------------------------------------------- state I/O
+// Host arrays are staged through device scratch in row chunks and packed/unpacked by
+// kernels (k_import_rows / k_export_rows), so host<->device copies are plain memcpys of the
+// reference's own array layouts.
+static int stage_rows(const spgg_handle *h) {
+  const long long budget = 32ll << 20;  // sites per chunk
+  return (int)std::max<long long>(1, std::min<long long>(h->g.rows, budget / h->g.L));
+}
+
+static int ensure_scratch(spgg_handle *h, bool want_q) {
+  const size_t n = (size_t)stage_rows(h) * h->g.L;
+  if (!h->d_sc_S) {
+    CUDA_TRY(cudaMalloc((void **)&h->d_sc_S, n));
+    CUDA_TRY(cudaMalloc((void **)&h->d_sc_R, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void **)&h->d_sc_info, 2 * sizeof(unsigned long long)));
+  }
+  if (want_q && !h->d_sc_Q) CUDA_TRY(cudaMalloc((void **)&h->d_sc_Q, n * 4 * sizeof(double)));
+  return SPGG_OK;
+}
+
+extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double *R, const double *Q) {
+  if (!h || !S || !R || !Q) return fail(SPGG_E_INVALID, "spgg_set_state: null argument");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rcode = ensure_scratch(h, true);
+  if (rcode) return rcode;
+  const Geom &g = h->g;
+  const RepConst &rc = h->rc_host[rep];
+  CUDA_TRY(cudaMemset(h->d_sc_info, 0, 2 * sizeof(unsigned long long)));
+  const int chunk = stage_rows(h);
+  for (int i0 = 0; i0 < g.rows; i0 += chunk) {
+    const int nr = std::min(chunk, g.rows - i0);
+    const size_t n = (size_t)nr * g.L, off = (size_t)i0 * g.L;
+    CUDA_TRY(cudaMemcpyAsync(h->d_sc_S, S + off, n, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_sc_R, R + off, n * sizeof(double), cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_sc_Q, Q + off * 4, n * 4 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    const int grid = (int)std::min<long long>(148 * 16, ((long long)nr * ((g.L + 31) / 32) * 32 + 255) / 256);
+#define IMPORT(Md) k_import_rows<Md><<<std::max(1, grid), 256>>>(g, rep, i0, nr, h->d_sc_S, h->d_sc_R, h->d_sc_Q, \
+                       h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->d_sc_info)
+    if (h->mode == MODE_F32_I8) IMPORT(ModeF32I8);
+    else if (h->mode == MODE_F32_F) IMPORT(ModeF32F);
+    else IMPORT(ModeF64);
+#undef IMPORT
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+  }
+  unsigned long long info[2];
+  CUDA_TRY(cudaMemcpy(info, h->d_sc_info, sizeof(info), cudaMemcpyDeviceToHost));
+  if (info[0] == 1) return fail(SPGG_E_INVALID, "strategy array holds values other than 0/1");
+  if (info[0] == 2)
+    return fail(SPGG_E_INVALID, "R is not representable in int8 units of %g; use r_storage=FP32", rc.rq);
+  if (rep == 0) h->iter = 0;
+  h->eps_cur[rep] = h->params[rep].epsilon;
+  int stop = -1;
+  if (g.wrap_rows && (info[1] == 0 || info[1] == (unsigned long long)g.site_stride))
+    stop = (int)h->iter;  // uniform start: iteration iter+1 breaks (spgg.py:405)
+  h->stop_at[rep] = stop;
+  CUDA_TRY(cudaMemcpy(h->d_stop + rep, &stop, sizeof(int), cudaMemcpyHostToDevice));
+  return SPGG_OK;
+}
+
+extern "C" int spgg_get_state(spgg_t *h, int rep, uint8_t *S, double *R, double *Q) {
+  if (!h) return fail(SPGG_E_INVALID, "null handle");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rcode = ensure_scratch(h, Q != nullptr);
+  if (rcode) return rcode;
+  const Geom &g = h->g;
+  const RepConst &rc = h->rc_host[rep];
+  const int chunk = stage_rows(h);
+  for (int i0 = 0; i0 < g.rows; i0 += chunk) {
+    const int nr = std::min(chunk, g.rows - i0);
+    const size_t n = (size_t)nr * g.L, off = (size_t)i0 * g.L;
+    const int grid = (int)std::min<long long>(148 * 16, ((long long)n + 255) / 256);
+#define EXPORT(Md) k_export_rows<Md><<<std::max(1, grid), 256>>>(g, rep, i0, nr, S ? h->d_sc_S : nullptr, \
+                       R ? h->d_sc_R : nullptr, Q ? h->d_sc_Q : nullptr, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq)
+    if (h->mode == MODE_F32_I8) EXPORT(ModeF32I8);
+    else if (h->mode == MODE_F32_F) EXPORT(ModeF32F);
+    else EXPORT(ModeF64);
+#undef EXPORT
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (S) CUDA_TRY(cudaMemcpyAsync(S + off, h->d_sc_S, n, cudaMemcpyDeviceToHost, 0));
+    if (R) CUDA_TRY(cudaMemcpyAsync(R + off, h->d_sc_R, n * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    if (Q) CUDA_TRY(cudaMemcpyAsync(Q + off * 4, h->d_sc_Q, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+  }
+  return SPGG_OK;
+}
+
+extern "C" int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const uint8_t *b) {
+  if (!h) return fail(SPGG_E_INVALID, "null handle");
+  if (h->n_rep != 1) return fail(SPGG_E_UNSUPPORTED, "replay draws are supported for a single replica");
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaFree(h->d_u); cudaFree(h->d_b);
+  h->d_u = nullptr; h->d_b = nullptr; h->replay_n = 0;
+  if (n_steps <= 0) return SPGG_OK;
+  if (!u || !b) return fail(SPGG_E_INVALID, "spgg_set_replay: null draw arrays");
+  const size_t n = (size_t)n_steps * h->g.site_stride;
+  CUDA_TRY(cudaMalloc((void **)&h->d_u, n * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&h->d_b, n));
+  CUDA_TRY(cudaMemcpy(h->d_u, u, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_b, b, n, cudaMemcpyHostToDevice));
+  h->replay_first = h->iter;
+  h->replay_n = n_steps;
+  return SPGG_OK;
+}
+
+// ---------------------------------------------------------------- stepping
+static int ensure_tables(spgg_handle *h, int n_steps) {
+  const int need = n_steps + 1;
+  if (need <= h->cap) return SPGG_OK;
+  cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_eps); cudaFree(h->d_thr);
+  h->d_gmax = nullptr; h->d_stats = nullptr; h->d_eps = nullptr; h->d_thr = nullptr;
+  h->cap = 0;
+  CUDA_TRY(cudaMalloc(&h->d_gmax, h->elem_val() * (size_t)h->n_rep * need));
+  CUDA_TRY(cudaMalloc((void **)&h->d_stats, sizeof(double) * (size_t)h->n_rep * need * NSTAT));
+  CUDA_TRY(cudaMalloc((void **)&h->d_eps, sizeof(double) * (size_t)h->n_rep * (need + 1)));
+  CUDA_TRY(cudaMalloc((void **)&h->d_thr, sizeof(uint32_t) * (size_t)h->n_rep * (need + 1)));
+  h->cap = need;
+  return SPGG_OK;
+}
+
+static uint32_t thr24(double eps) {
+  double t = std::ceil(eps * 16777216.0);
+  if (t < 0) t = 0;
+  if (t > 16777216.0) t = 16777216.0;
+  return (uint32_t)t;
+}
+
+extern "C" int spgg_begin_steps(spgg_t *h, int n_steps, void *stream_) {
+  if (!h) return fail(SPGG_E_INVALID, "null handle");
+  if (n_steps < 1) return fail(SPGG_E_INVALID, "n_steps must be >= 1");
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream_;
+  rcode = ensure_tables(h, n_steps);
+  if (rcode) return rcode;
+  // eps used at iteration iter+idx, idx = 1..n_steps (+1 spare entry); algorithms.py:40-42
+  std::vector<double> &eps = h->eps_host;   // kept alive by the handle: the copies are async
+  std::vector<uint32_t> &thr = h->thr_host;
+  eps.assign((size_t)(h->cap + 1) * h->n_rep, 0.0);
+  thr.assign(eps.size(), 0u);
+  for (int r = 0; r < h->n_rep; ++r) {
+    double e = h->eps_cur[r];
+    for (int idx = 1; idx <= n_steps + 1 && idx <= h->cap; ++idx) {
+      eps[(size_t)idx * h->n_rep + r] = e;
+      thr[(size_t)idx * h->n_rep + r] = thr24(e);
+      e = std::max(e * h->params[r].epsilon_decay, h->params[r].epsilon_min);
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_eps, eps.data(), eps.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_thr, thr.data(), thr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(h->d_gmax, 0, h->elem_val() * (size_t)h->n_rep * h->cap, st));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * (size_t)h->n_rep * h->cap * NSTAT, st));
+  h->pending = true;
+  h->pend_t0 = h->iter;
+  h->pend_n = n_steps;
+  h->pend_cur0 = h->cur;
+  h->pend_rel = 0;
+  h->pend_stream = st;
+  return SPGG_OK;
+}
+
+// one k_step launch at relative index pend_rel (finishing iteration pend_t0+pend_rel)
+extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *stream_) {
+  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_phase_kernel outside begin/end");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const long long j = h->pend_t0 + h->pend_rel;
+  const long long draw = j - h->replay_first;  // draws of iteration j+1 are entry `draw`
+  const bool replay = do_select && h->d_u && draw >= 0 && draw < h->replay_n;
+  KArgs a;
+  a.g = h->g;
+  a.rc = h->d_rc;
+  a.Q = h->d_Q;
+  a.R_in = h->d_R[h->cur]; a.R_out = h->d_R[h->cur ^ 1];
+  a.code_in = h->d_code[h->cur]; a.code_out = h->d_code[h->cur ^ 1];
+  a.S_in = h->d_S[h->cur]; a.S_out = h->d_S[h->cur ^ 1];
+  a.gmax = h->d_gmax; a.stats = h->d_stats; a.partials = h->d_partials;
+  a.tickets = h->d_tickets; a.stop_at = h->d_stop;
+  a.eps_tab = h->d_eps; a.thr_tab = h->d_thr;
+  a.u = replay ? h->d_u + (size_t)draw * h->g.site_stride : nullptr;
+  a.b = replay ? h->d_b + (size_t)draw * h->g.site_stride : nullptr;
+  a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
+  a.do_update = do_update; a.do_select = do_select;
+  step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
+  f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_step, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  if (do_select) h->cur ^= 1;
+  return SPGG_OK;
+}
+
+// gmax of the iteration about to be finished (pend_rel+1); advances pend_rel
+extern "C" int spgg_phase_gmax(spgg_t *h, void *stream_) {
+  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_phase_gmax outside begin/end");
+  cudaStream_t st = (cudaStream_t)stream_;
+  h->pend_rel += 1;
+  GArgs a;
+  a.g = h->g;
+  a.rc = h->d_rc;
+  a.code_in = h->d_code[h->cur];
+  a.gmax = h->d_gmax;
+  a.stop_at = h->d_stop;
+  a.j = (int)(h->pend_t0 + h->pend_rel); a.rel = h->pend_rel; a.cap = h->cap;
+  gmax_fn_t f = pick_gmax(h->mode, h->M);
+  f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_gmax, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return SPGG_OK;
+}
+
+extern "C" void *spgg_gmax_device_ptr(spgg_t *h) {
+  if (!h || !h->pending) return nullptr;
+  return (char *)h->d_gmax + h->elem_val() * (size_t)h->pend_rel;  // replica 0
+}
+
+extern "C" int spgg_end_steps(spgg_t *h, void *stream_) {
+  (void)stream_;
+  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_end_steps without spgg_begin_steps");
+  return SPGG_OK;  // bookkeeping is finished lazily by the next synchronising call
+}
+
+extern "C" int spgg_step(spgg_t *h, int n_steps, void *stream_) {
+  int rcode = spgg_begin_steps(h, n_steps, stream_);
+  if (rcode) return rcode;
+  rcode = spgg_phase_kernel(h, 0, 1, stream_);  // choose the action of iteration iter+1
+  for (int s = 1; s <= n_steps && !rcode; ++s) {
+    rcode = spgg_phase_gmax(h, stream_);
+    if (!rcode) rcode = spgg_phase_kernel(h, 1, s < n_steps ? 1 : 0, stream_);
+  }
+  if (rcode) return rcode;
+  return spgg_end_steps(h, stream_);
+}
+
+extern "C" int spgg_get_stats(spgg_t *h, int rep, int first, int n, double *rows_out) {
+  if (!h || !rows_out) return fail(SPGG_E_INVALID, "spgg_get_stats: null argument");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  if (first < 0 || n < 0 || first + n > h->cap) return fail(SPGG_E_INVALID, "rows [%d,%d) outside the last chunk (%d rows)", first, first + n, h->cap);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(rows_out, h->d_stats + ((size_t)rep * h->cap + first) * NSTAT,
+                      sizeof(double) * (size_t)n * NSTAT, cudaMemcpyDeviceToHost));
+  return SPGG_OK;
+}
+
+extern "C" int spgg_query(spgg_t *h, int rep, spgg_status_t *out) {
+  if (!h || !out) return fail(SPGG_E_INVALID, "spgg_query: null argument");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  out->iteration = (h->stop_at[rep] >= 0 && h->stop_at[rep] < h->iter) ? h->stop_at[rep] : h->iter;
+  out->stopped_at = h->stop_at[rep];
+  out->epsilon = h->eps_cur[rep];
+  out->n_replicas = h->n_rep;
+  out->r_is_int8 = h->mode == MODE_F32_I8;
+  out->kernel_launches = h->launches;
+  return SPGG_OK;
+}
+
+// device-side random initial state (distributions of spgg.py:121,129,162)
+extern "C" int spgg_init_random(spgg_t *h, int rep, uint64_t seed) {
+  if (!h) return fail(SPGG_E_INVALID, "null handle");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+  const int grid = 148 * 8;
+  if (h->mode == MODE_F32_I8) k_init_random<ModeF32I8><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi);
+  else if (h->mode == MODE_F32_F) k_init_random<ModeF32F><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi);
+  else k_init_random<ModeF64><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->launches += 1;
+  if (rep == 0) h->iter = 0;
+  h->eps_cur[rep] = h->params[rep].epsilon;
+  int stop = -1;
+  h->stop_at[rep] = -1;
+  CUDA_TRY(cudaMemcpy(h->d_stop + rep, &stop, sizeof(int), cudaMemcpyHostToDevice));
+  return SPGG_OK;
+}
+
+// ---------------------------------------------------------------- strips
+extern "C" int64_t spgg_halo_bytes(spgg_t *h) {
+  if (!h) return 0;
+  const Geom &g = h->g;
+  const int64_t per_rep = (int64_t)GH * g.pitchB * (int64_t)(h->elem_code() + h->elem_R()) + (int64_t)GH * g.pitchW * 4;
+  return per_rep * h->n_rep;
+}
+
+template <class Md>
+static void launch_pack(spgg_handle *h, void *up, void *down, cudaStream_t st) {
+  const long long rep_bytes = spgg_halo_bytes(h) / h->n_rep;
+  dim3 grid(std::max(1, std::min(64, (GH * h->g.pitchB + 255) / 256)), h->n_rep);
+  k_halo_pack<Md><<<grid, 256, 0, st>>>(h->g, h->d_code[h->cur], h->d_R[h->cur], h->d_S[h->cur],
+                                        (unsigned char *)up, (unsigned char *)down, rep_bytes);
+}
+template <class Md>
+static void launch_unpack(spgg_handle *h, const void *up, const void *down, cudaStream_t st) {
+  const long long rep_bytes = spgg_halo_bytes(h) / h->n_rep;
+  dim3 grid(std::max(1, std::min(64, (GH * h->g.pitchB + 255) / 256)), h->n_rep);
+  k_halo_unpack<Md><<<grid, 256, 0, st>>>(h->g, h->d_code[h->cur], h->d_R[h->cur], h->d_S[h->cur],
+                                          (const unsigned char *)up, (const unsigned char *)down, rep_bytes);
+}
+
+extern "C" int spgg_halo_pack(spgg_t *h, void *to_up, void *to_down, void *stream_) {
+  if (!h || !to_up || !to_down) return fail(SPGG_E_INVALID, "spgg_halo_pack: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (h->mode == MODE_F32_I8) launch_pack<ModeF32I8>(h, to_up, to_down, st);
+  else if (h->mode == MODE_F32_F) launch_pack<ModeF32F>(h, to_up, to_down, st);
+  else launch_pack<ModeF64>(h, to_up, to_down, st);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return SPGG_OK;
+}
+
+extern "C" int spgg_halo_unpack(spgg_t *h, const void *from_up, const void *from_down, void *stream_) {
+  if (!h || !from_up || !from_down) return fail(SPGG_E_INVALID, "spgg_halo_unpack: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (h->mode == MODE_F32_I8) launch_unpack<ModeF32I8>(h, from_up, from_down, st);
+  else if (h->mode == MODE_F32_F) launch_unpack<ModeF32F>(h, from_up, from_down, st);
+  else launch_unpack<ModeF64>(h, from_up, from_down, st);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return SPGG_OK;
+}

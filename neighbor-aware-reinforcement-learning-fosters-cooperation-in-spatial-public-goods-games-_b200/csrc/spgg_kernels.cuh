@@ -1,0 +1,981 @@
+// SPGG lattice step for sm_100a - kernels.
+//
+// One iteration t of the reference loop (src/model/spgg.py:368-592, Q-learning
+// rule src/model/algorithms.py:96-133) is split along its data dependencies
+// (DESIGN.md "step decomposition"):
+//
+//   k_gmax<t>   light: reads the per-site reward codes of iteration t, produces the
+//               lattice-global max |reward difference|           (spgg.py:486-488)
+//   k_step<t>   heavy, fused: finishes iteration t (TD update algorithms.py:122-131,
+//               neighbour-aware update spgg.py:478-509, statistics spgg.py:512-592)
+//               while Q is in registers, then - because the post-action state of
+//               iteration t is the pre-action state of t+1 (spgg.py:423 vs 409) -
+//               chooses the action of iteration t+1 (algorithms.py:102-110), updates
+//               the reputation (spgg.py:319-323) and emits the reward code of t+1.
+//
+// Q is read once and written once per iteration; R, the strategy bits and the
+// one-byte reward code are the only other per-site traffic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spgg {
+
+constexpr int GH = 2;            // ghost rows on each side of every lattice plane
+constexpr int TC = 128;          // tile columns: one warp covers a 128-site row segment
+constexpr int HP = 4;            // smem column pad on each side (>= widest halo)
+constexpr int SMW = TC + 2 * HP; // smem row stride (elements)
+constexpr int HR = 2;            // smem row halo (rows) on each side
+constexpr int NSTAT = 40;
+constexpr int MAX_THREADS = 256;
+
+// stat-row columns (mirror of include/spgg.h)
+enum {
+  ST_NC_OLD = 0, ST_N_CD = 1, ST_N_DC = 2, ST_NC_NEW = 3, ST_SUM_P = 4, ST_SUM_P_C = 5,
+  ST_SUM_P_D = 6, ST_SUM_WP_P = 7, ST_SUM_REW_C = 8, ST_SUM_REW_D = 9, ST_SUM_RATIO = 10,
+  ST_GROUP0 = 11, ST_SUM_R = 17, ST_SUM_Q = 18, ST_SUM_Q_C = 22, ST_SUM_Q_D = 26,
+  ST_SUM_NI = 30, ST_N_BEST_POS = 31, ST_N_BEST_2ND = 32, ST_GMAX = 33,
+  // scratch columns used between the per-CTA partials and the final row (fp32 mode)
+  ST_X_SN0 = 34, /* 34..37: sum of SigmaN per class (C_old*2+coop) */
+  ST_X_NSEL = 38 /* #cooperating actions chosen by the select phase */
+};
+
+// neighbour offsets (dx,dy), reference order spgg.py:479-485; neighbour k of (i,j) is
+// (i-dx, j-dy) because np.roll(X,(dx,dy))[i,j] == X[i-dx, j-dy].
+__device__ __constant__ const int8_t c_off[12][2] = {
+    {1, 0}, {-1, 0}, {0, 1}, {0, -1}, {2, 0}, {-2, 0},
+    {0, 2}, {0, -2}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+
+// per-replica constants, built on the host (spgg_capi.cu: build_repconst)
+struct RepConst {
+  float rewtab[128];   // fp32 mode reward by (SigmaN<<2 | C_old<<1 | coop_new)
+  float ratiotab[128]; // fp32 mode |wR*.5|/(|rew|+1e-9)*100 for coop codes, else 0
+  double g[6];         // rc*n/5                                     spgg.py:256
+  double cost, lo, span, wP, wR, rc;
+  double alpha, gamma, kappa, leps;
+  double gainC, lossD, rmin, rmax; // reputation step / clip, real units   spgg.py:321-323
+  double rq;                       // int8 quantum: R_real = R_int8 * rq
+  float alpha_f, gamma_f, kappa_f, leps_f;
+  float gainC_f, lossD_f, rmin_f, rmax_f;
+  int gain_i, loss_i, rmin_i, rmax_i;
+  uint32_t seed_lo, seed_hi;
+  int has_ratio;
+  int pad_;
+};
+
+struct Geom {
+  int L, rows, row0, wrap_rows;
+  int pitchB;   // elements per row of the byte planes (code, R)
+  int pitchW;   // 32-bit words per row of the strategy bit plane
+  int n_tx, n_ty, TR;
+  int ctas_per_rep, n_rep;
+  long long plane_stride; // elements per replica, (rows+2GH)*pitchB
+  long long bits_stride;  // words per replica, (rows+2GH)*pitchW
+  long long site_stride;  // sites per replica, rows*L
+};
+
+struct KArgs {
+  Geom g;
+  const RepConst *rc;
+  void *Q;
+  const void *R_in;
+  void *R_out;
+  const void *code_in;
+  void *code_out;
+  const uint32_t *S_in;
+  uint32_t *S_out;
+  const void *gmax;        // Val[n_rep][cap]
+  double *stats;           // [n_rep][cap][NSTAT]
+  double *partials;        // [n_rep][ctas_per_rep][NSTAT]
+  unsigned *tickets;       // [n_rep]
+  int *stop_at;            // [n_rep], -1 = running
+  const double *eps_tab;   // [cap+1][n_rep]: eps used at iteration (start + idx)
+  const uint32_t *thr_tab; // same shape, ceil(eps*2^24)
+  const double *u;         // replay draws of iteration j+1 (or nullptr)
+  const uint8_t *b;
+  int j;                   // absolute iteration index this launch finishes (state index)
+  int rel;                 // j - (iteration at start of the spgg_step call)
+  int cap;                 // rows per replica in stats/gmax tables
+  int do_update, do_select;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ------------------------------------------------------------------ modes
+// Reward code of a site for iteration t (one per site, written by k_step<t-1>):
+//   bit0 = s_t   (state in which a_t was chosen)            spgg.py:409
+//   bit1 = coop_t (a_t == 0)                                algorithms.py:109
+//   bit2 = C_{t-1} (S_{t-1} == 0, the strategy the payoff P refers to)  spgg.py:373
+//   fp32 mode: bits 3..7 = SigmaN = sum over the site's 5 groups of #cooperators (0..25)
+//   fp64 mode: bits 3..17 = N of the 5 groups in the reference's summation order
+//              (centres (i,j),(i-1,j),(i+1,j),(i,j-1),(i,j+1); spgg.py:373-377), 3 bits each
+struct ModeF32I8 {
+  typedef float Q; typedef int8_t R; typedef uint8_t Code; typedef float Val;
+  static constexpr bool kFp64 = false;
+};
+struct ModeF32F {
+  typedef float Q; typedef float R; typedef uint8_t Code; typedef float Val;
+  static constexpr bool kFp64 = false;
+};
+struct ModeF64 {
+  typedef double Q; typedef double R; typedef uint32_t Code; typedef double Val;
+  static constexpr bool kFp64 = true;
+};
+
+template <class Md>
+__device__ __forceinline__ typename Md::Code pack_code(const int (&n)[5], int C, int coop, int s) {
+  if constexpr (Md::kFp64) {
+    return (typename Md::Code)((n[0] << 15) | (n[1] << 12) | (n[2] << 9) | (n[3] << 6) |
+                               (n[4] << 3) | (C << 2) | (coop << 1) | s);
+  } else {
+    return (typename Md::Code)(((n[0] + n[1] + n[2] + n[3] + n[4]) << 3) | (C << 2) |
+                               (coop << 1) | s);
+  }
+}
+
+// normalised payoff P of a site from its code, fp64, reference operation order
+// (spgg.py:256-257 per group, summed left to right spgg.py:373-377, normalised :377)
+__device__ __forceinline__ double payoff_f64(uint32_t code, const RepConst &rc) {
+  const double C = (double)((code >> 2) & 1u), D = 1.0 - C;
+  double tot = 0.0;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const double share = rc.g[(code >> (15 - 3 * q)) & 7u];
+    const double term =
+        __dadd_rn(__dmul_rn(__dsub_rn(share, rc.cost), C), __dmul_rn(share, D));
+    tot = (q == 0) ? term : __dadd_rn(tot, term);
+  }
+  return __ddiv_rn(__dsub_rn(tot, rc.lo), rc.span);
+}
+// reward spgg.py:424-427
+__device__ __forceinline__ double reward_f64(uint32_t code, double P, const RepConst &rc) {
+  const double rr = ((code >> 1) & 1u) ? 0.5 : 0.0;
+  return __dadd_rn(__dmul_rn(rc.wP, P), __dmul_rn(rc.wR, rr));
+}
+
+template <class Md>
+__device__ __forceinline__ typename Md::Val val_of_code(typename Md::Code code, const RepConst &rc,
+                                                        const float *sm_tab) {
+  if constexpr (Md::kFp64) {
+    return reward_f64(code, payoff_f64(code, rc), rc);
+  } else {
+    return sm_tab[code >> 1];
+  }
+}
+
+// reputation state spgg.py:292-307: (sum over self + offsets of R)/n > 0, reference order
+template <class RT, int M>
+__device__ __forceinline__ int rep_state(const RT *smR, int sr, int sc) {
+  constexpr int NK = (M == 2) ? 12 : 4;
+  if constexpr (sizeof(RT) == 1) {
+    int acc = smR[sr * SMW + sc];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) acc += smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])];
+    return acc > 0;
+  } else if constexpr (sizeof(RT) == 4) {
+    float acc = smR[sr * SMW + sc];
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      acc = __fadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
+    return __fdiv_rn(acc, (float)(NK + 1)) > 0.0f;
+  } else {
+    double acc = smR[sr * SMW + sc];
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      acc = __dadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
+    return __ddiv_rn(acc, (double)(NK + 1)) > 0.0;
+  }
+}
+
+__device__ __forceinline__ int wrap_col(int col, int L) {
+  if (col < 0) {
+    col += L;
+    if (col < 0) col = ((col % L) + L) % L;
+  } else if (col >= L) {
+    col -= L;
+    if (col >= L) col %= L;
+  }
+  return col;
+}
+
+// generic tile loader: plane element (prow, col) for the tile rows [r0-H, r0+TR+H) and
+// columns [c0-H, c0+TC+H) into smem[(rr+HR)*SMW + cc+HP]; columns wrap, rows use ghosts.
+template <class T, int H>
+__device__ __forceinline__ void load_tile(T *sm, const T *plane, const Geom &g, int r0, int c0,
+                                          int TR) {
+  constexpr int NC = TC + 2 * H;
+  const int nr = TR + 2 * H;
+  for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
+    const int rr = e / NC - H, cc = e % NC - H;
+    const int prow = r0 + rr + GH;
+    T v = T(0);
+    if (prow >= 0 && prow < g.rows + 2 * GH) {
+      const int col = wrap_col(c0 + cc, g.L);
+      v = plane[(long long)prow * g.pitchB + col];
+    }
+    sm[(rr + HR) * SMW + cc + HP] = v;
+  }
+}
+
+// strategy bits -> cooperator flags (1 = cooperator), halo 2
+__device__ __forceinline__ void load_coop_tile(uint8_t *sm, const uint32_t *bits, const Geom &g,
+                                               int r0, int c0, int TR) {
+  constexpr int H = 2, NC = TC + 2 * H;
+  const int nr = TR + 2 * H;
+  for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
+    const int rr = e / NC - H, cc = e % NC - H;
+    const int prow = r0 + rr + GH;
+    uint8_t v = 0;
+    if (prow >= 0 && prow < g.rows + 2 * GH) {
+      const int col = wrap_col(c0 + cc, g.L);
+      const uint32_t w = bits[(long long)prow * g.pitchW + (col >> 5)];
+      v = (uint8_t)(((w >> (col & 31)) & 1u) ^ 1u);
+    }
+    sm[(rr + HR) * SMW + cc + HP] = v;
+  }
+}
+
+// deterministic block reduction of NV doubles held per thread; result in sm_red[0..NV)
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *sm_red /* [8][NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm_red[warp * NV + i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = 0.0;
+    for (int w = 0; w < nw; ++w) x += sm_red[w * NV + threadIdx.x];
+    sm_red[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// =================================================================== k_gmax
+struct GArgs {
+  Geom g;
+  const RepConst *rc;
+  const void *code_in;
+  void *gmax;          // Val[n_rep][cap], zeroed at the start of the spgg_step call
+  const int *stop_at;
+  int j, rel, cap;
+};
+
+template <class Md, int M>
+__global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
+  typedef typename Md::Code Code;
+  typedef typename Md::Val Val;
+  constexpr int NK = (M == 2) ? 12 : 4;
+  const Geom &g = a.g;
+  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  Val *sm_val = reinterpret_cast<Val *>(smem);
+  float *sm_tab = reinterpret_cast<float *>(smem + align_up(sizeof(Val) * (g.TR + 2 * HR) * SMW, 16));
+  __shared__ RepConst s_rc;
+  for (int i = threadIdx.x; i < (int)(sizeof(RepConst) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  __syncthreads();
+  if (!Md::kFp64)
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) sm_tab[i] = s_rc.rewtab[i];
+
+  const Code *code_in = reinterpret_cast<const Code *>(a.code_in) + (long long)rep * g.plane_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  Val lmax = Val(0);
+
+  const int n_tiles = g.n_tx * g.n_ty;
+  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep) {
+    const int r0 = (tile / g.n_tx) * g.TR, c0 = (tile % g.n_tx) * TC;
+    __syncthreads();
+    {
+      constexpr int NC = TC + 2 * M;
+      const int nr = g.TR + 2 * M;
+      for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
+        const int rr = e / NC - M, cc = e % NC - M;
+        const int prow = r0 + rr + GH;
+        Val v = Val(0);
+        if (prow >= 0 && prow < g.rows + 2 * GH) {
+          const int col = wrap_col(c0 + cc, g.L);
+          v = val_of_code<Md>(code_in[(long long)prow * g.pitchB + col], s_rc, sm_tab);
+        }
+        sm_val[(rr + HR) * SMW + cc + HP] = v;
+      }
+    }
+    __syncthreads();
+    for (int rr = warp; rr < g.TR; rr += nw) {
+      if (r0 + rr >= g.rows) break;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int cc = k4 * 32 + lane;
+        if (c0 + cc >= g.L) continue;
+        const int sr = rr + HR, sc = cc + HP;
+        const Val vx = sm_val[sr * SMW + sc];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const Val vk = sm_val[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])];
+          Val d;
+          if constexpr (Md::kFp64) d = fabs(__dsub_rn(vk, vx));
+          else d = fabsf(__fsub_rn(vk, vx));
+          lmax = d > lmax ? d : lmax;
+        }
+      }
+    }
+  }
+  // block max -> one atomic per CTA (non-negative IEEE values order like unsigned ints)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const Val other = __shfl_down_sync(0xffffffffu, lmax, o);
+    lmax = other > lmax ? other : lmax;
+  }
+  __shared__ Val s_wmax[MAX_THREADS / 32];
+  if (lane == 0) s_wmax[warp] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Val m = s_wmax[0];
+    for (int w = 1; w < nw; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
+    Val *dst = reinterpret_cast<Val *>(a.gmax) + (long long)rep * a.cap + a.rel;
+    if constexpr (Md::kFp64)
+      atomicMax(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)__double_as_longlong(m));
+    else
+      atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(m));
+  }
+}
+
+
+// =================================================================== k_step
+template <class Md>
+struct SmemLayout {
+  size_t off_code, off_val, off_R, off_C, off_N, off_tab, off_red, total;
+  __host__ __device__ explicit SmemLayout(int TR) {
+    const size_t n = (size_t)(TR + 2 * HR) * SMW;
+    size_t o = 0;
+    off_val = o;  o = (o + sizeof(typename Md::Val) * n + 15) / 16 * 16;
+    off_R = o;    o = (o + sizeof(typename Md::R) * n + 15) / 16 * 16;
+    off_code = o; o = (o + sizeof(typename Md::Code) * n + 15) / 16 * 16;
+    off_C = o;    o = (o + n + 15) / 16 * 16;
+    off_N = o;    o = (o + n + 15) / 16 * 16;
+    off_tab = o;  o = (o + 256 * sizeof(float) + 15) / 16 * 16;
+    off_red = o;  o = (o + sizeof(double) * (MAX_THREADS / 32) * NSTAT + 15) / 16 * 16;
+    total = o;
+  }
+};
+
+template <class T>
+__device__ __forceinline__ T sel4(int e, T a0, T a1, T a2, T a3) {
+  const T lo = (e & 1) ? a1 : a0, hi = (e & 1) ? a3 : a2;
+  return (e & 2) ? hi : lo;
+}
+
+template <class Md, int M, bool ACTION, bool REPLAY>
+__global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
+  typedef typename Md::Q QT;
+  typedef typename Md::R RT;
+  typedef typename Md::Code Code;
+  typedef typename Md::Val Val;
+  constexpr int NK = (M == 2) ? 12 : 4;
+  constexpr bool kI8 = (sizeof(RT) == 1);
+  const Geom &g = a.g;
+  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  const bool upd = a.do_update != 0;
+  const bool sel = (a.do_select != 0) && !(stop >= 0 && a.j == stop);
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout<Md> lay(g.TR);
+  Val *sm_val = reinterpret_cast<Val *>(smem + lay.off_val);
+  RT *sm_R = reinterpret_cast<RT *>(smem + lay.off_R);
+  Code *sm_code = reinterpret_cast<Code *>(smem + lay.off_code);
+  uint8_t *sm_C = smem + lay.off_C;
+  uint8_t *sm_N = smem + lay.off_N;
+  float *sm_tab = reinterpret_cast<float *>(smem + lay.off_tab);
+  float *sm_ratio = sm_tab + 128;
+  double *sm_red = reinterpret_cast<double *>(smem + lay.off_red);
+  __shared__ RepConst s_rc;
+  __shared__ int s_is_last;
+
+  for (int i = threadIdx.x; i < (int)(sizeof(RepConst) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    sm_tab[i] = s_rc.rewtab[i];
+    sm_ratio[i] = s_rc.ratiotab[i];
+  }
+  const RepConst &rc = s_rc;
+
+  QT *Qp = reinterpret_cast<QT *>(a.Q) + (long long)rep * g.site_stride * 4;
+  const RT *R_in = reinterpret_cast<const RT *>(a.R_in) + (long long)rep * g.plane_stride;
+  RT *R_out = reinterpret_cast<RT *>(a.R_out) + (long long)rep * g.plane_stride;
+  const Code *code_in = reinterpret_cast<const Code *>(a.code_in) + (long long)rep * g.plane_stride;
+  Code *code_out = reinterpret_cast<Code *>(a.code_out) + (long long)rep * g.plane_stride;
+  const uint32_t *S_in = a.S_in + (long long)rep * g.bits_stride;
+  uint32_t *S_out = a.S_out + (long long)rep * g.bits_stride;
+
+  // scalars of this launch
+  Val inv_den = Val(0), den = Val(1);
+  if (upd) {
+    const Val gm = reinterpret_cast<const Val *>(a.gmax)[(long long)rep * a.cap + a.rel];
+    if constexpr (Md::kFp64) den = __dadd_rn(gm, rc.leps);  // spgg.py:489 denominator
+    else inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));
+  }
+  const long long tab_idx = (long long)(a.rel + 1) * g.n_rep + rep;
+  const uint32_t thr = sel ? a.thr_tab[tab_idx] : 0u;
+  const double eps = (sel && REPLAY) ? a.eps_tab[tab_idx] : 0.0;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  // per-thread statistics (exact integers, doubles folded once per tile)
+  unsigned long long cls_n[4] = {0, 0, 0, 0};   // by class = C_old*2 + coop
+  unsigned long long cls_sn[4] = {0, 0, 0, 0};  // fp32 mode: sum of SigmaN per class
+  unsigned long long grp[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long n_best = 0, n_best2 = 0, n_sel_coop = 0;
+  double sumQ[4] = {0, 0, 0, 0}, sumQC[4] = {0, 0, 0, 0};
+  double sumNI = 0.0, sumR = 0.0, sumRatio = 0.0;
+  double sumP = 0, sumPC = 0, sumPD = 0, sumWP = 0, sumRewC = 0, sumRewD = 0;  // fp64 mode
+
+  const int n_tiles = g.n_tx * g.n_ty;
+  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep) {
+    const int r0 = (tile / g.n_tx) * g.TR, c0 = (tile % g.n_tx) * TC;
+    __syncthreads();
+    // ---- stage tiles + halos
+    if (upd) load_tile<Code, M>(sm_code, code_in, g, r0, c0, g.TR);
+    load_tile<RT, ACTION ? 0 : M>(sm_R, R_in, g, r0, c0, g.TR);
+    load_coop_tile(sm_C, S_in, g, r0, c0, g.TR);
+    __syncthreads();
+    if (upd) {
+      constexpr int NC = TC + 2 * M;
+      const int nr = g.TR + 2 * M;
+      for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
+        const int idx = (e / NC - M + HR) * SMW + (e % NC - M + HP);
+        sm_val[idx] = val_of_code<Md>(sm_code[idx], rc, sm_tab);
+      }
+    }
+    {
+      // N = cooperators in the 5-site group centred on each site (spgg.py:23-36) of S_j,
+      // for the tile and a one-site ring
+      constexpr int NC = TC + 2;
+      const int nr = g.TR + 2;
+      for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
+        const int idx = (e / NC - 1 + HR) * SMW + (e % NC - 1 + HP);
+        sm_N[idx] = (uint8_t)(sm_C[idx] + sm_C[idx + SMW] + sm_C[idx - SMW] + sm_C[idx + 1] +
+                              sm_C[idx - 1]);
+      }
+    }
+    __syncthreads();
+
+    // per-tile packed counters (flushed below): 8-bit class counts, 16-bit SigmaN sums,
+    // 10-bit group histogram; a thread sees at most 4*TR/nw <= 64 sites per tile
+    unsigned pk_n = 0;
+    unsigned long long pk_sn = 0, pk_grp = 0;
+    float tq[4] = {0.f, 0.f, 0.f, 0.f}, tqc[4] = {0.f, 0.f, 0.f, 0.f};
+    float tni = 0.f, tratio = 0.f, trf = 0.f;
+    int tri = 0;
+
+    // ---- per-site work: warp = one 128-site row segment, lane = 4 sites strided by 32
+    for (int rr = warp; rr < g.TR; rr += nw) {
+      const int i = r0 + rr;
+      if (i >= g.rows) break;
+      const int sr = rr + HR;
+      uint32_t w4[4] = {0, 0, 0, 0};
+      if (sel && !REPLAY) {
+        // counter = (column group, global row, iteration, 0); one call -> 4 sites
+        philox4x32_10((uint32_t)(((c0 >> 7) << 5) | lane), (uint32_t)(g.row0 + i),
+                      (uint32_t)(a.j + 1), 0u, rc.seed_lo, rc.seed_hi, w4);
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int cc = k4 * 32 + lane;
+        const int col = c0 + cc;
+        const bool valid = col < g.L;
+        const int sc = cc + HP;
+        const int sidx = sr * SMW + sc;
+        int a_new = 0;
+        if (valid) {
+          const long long site = (long long)i * g.L + col;
+          QT q0_, q1_, q2_, q3_;
+          if constexpr (Md::kFp64) {
+            const double2 lo2 = reinterpret_cast<const double2 *>(Qp)[site * 2];
+            const double2 hi2 = reinterpret_cast<const double2 *>(Qp)[site * 2 + 1];
+            q0_ = lo2.x; q1_ = lo2.y; q2_ = hi2.x; q3_ = hi2.y;
+          } else {
+            const float4 v = reinterpret_cast<const float4 *>(Qp)[site];
+            q0_ = v.x; q1_ = v.y; q2_ = v.z; q3_ = v.w;
+          }
+          const RT r_old = sm_R[sidx];
+          const int Ccur = sm_C[sidx];
+          // post-action state of iteration j == pre-action state of iteration j+1
+          const int s_new = ACTION ? Ccur : rep_state<RT, M>(sm_R, sr, sc);
+          if constexpr (kI8) tri += (int)r_old;
+          else if constexpr (sizeof(RT) == 4) trf += r_old;
+          else sumR += r_old;
+
+          if (upd) {
+            const Code code = sm_code[sidx];
+            const int s = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
+            const int act = coop ^ 1;
+            const Val vx = sm_val[sidx];
+            // neighbour-aware term inputs: spgg.py:486-494 (first arg-max wins)
+            Val best = Val(0);
+            int bidx = sidx, kstar = 0;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+              const int nidx = (sr - c_off[k][0]) * SMW + (sc - c_off[k][1]);
+              const Val vk = sm_val[nidx];
+              Val d;
+              if constexpr (Md::kFp64) d = __dsub_rn(vk, vx);
+              else d = __fsub_rn(vk, vx);
+              if (k == 0 || d > best) { best = d; bidx = nidx; kstar = k; }
+            }
+            const bool same = (((sm_code[bidx] >> 1) & 1u) == (unsigned)coop);
+            const int e = 2 * s + act;
+            const QT qe = sel4<QT>(e, q0_, q1_, q2_, q3_);
+            const QT na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
+            QT qtd, qfin;
+            if constexpr (Md::kFp64) {
+              const double mx = fmax(na, nb);
+              const double td = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, mx)), qe);  // algorithms.py:128
+              qtd = __dadd_rn(qe, __dmul_rn(rc.alpha, td));                              // algorithms.py:131
+              const double lam = __ddiv_rn(__dmul_rn(rc.kappa, fmax(0.0, best)), den);   // spgg.py:489
+              const double nu = same ? lam : -lam;                                       // spgg.py:494-495
+              // TD error on the table after the TD write (spgg.py:446-473)
+              const double na2 = (s_new == s && act == 0) ? qtd : na;
+              const double nb2 = (s_new == s && act == 1) ? qtd : nb;
+              const double td2 = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, fmax(na2, nb2))), qtd);
+              qfin = __dadd_rn(qtd, nu);                                                 // spgg.py:509
+              const double an = fabs(nu);
+              sumNI += __dmul_rn(
+                  __ddiv_rn(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)),
+                  100.0);                                                                // spgg.py:512
+              const double P = payoff_f64(code, rc);
+              sumP += P;
+              if (wasC) sumPC += P; else sumPD += P;
+              sumWP += __dmul_rn(rc.wP, P);
+              if (coop) {
+                sumRewC += vx;
+                sumRatio += __dmul_rn(
+                    __ddiv_rn(fabs(__dmul_rn(rc.wR, 0.5)), __dadd_rn(fabs(vx), 1e-9)), 100.0);
+              } else {
+                sumRewD += vx;
+              }
+            } else {
+              const float mx = fmaxf(na, nb);
+              const float td = __fsub_rn(__fmaf_rn(rc.gamma_f, mx, vx), qe);
+              qtd = __fmaf_rn(rc.alpha_f, td, qe);
+              const float lam = __fmul_rn(__fmul_rn(rc.kappa_f, fmaxf(0.0f, best)), inv_den);
+              const float nu = same ? lam : -lam;
+              const float na2 = (s_new == s && act == 0) ? qtd : na;
+              const float nb2 = (s_new == s && act == 1) ? qtd : nb;
+              const float td2 = __fsub_rn(__fmaf_rn(rc.gamma_f, fmaxf(na2, nb2), vx), qtd);
+              qfin = __fadd_rn(qtd, nu);
+              const float an = fabsf(nu);
+              tni += __fdividef(an, fabsf(rc.alpha_f * td2) + an + 1e-8f) * 100.0f;
+              pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
+              if (rc.has_ratio && coop) tratio += sm_ratio[code >> 1];
+            }
+            q0_ = (e == 0) ? qfin : q0_;
+            q1_ = (e == 1) ? qfin : q1_;
+            q2_ = (e == 2) ? qfin : q2_;
+            q3_ = (e == 3) ? qfin : q3_;
+            pk_n += 1u << (8 * (wasC * 2 + coop));
+            if (best > Val(0)) { n_best += 1u; n_best2 += (kstar >= 4); }
+            pk_grp += 1ull << (10 * (5 - (int)sm_N[sidx]));                              // spgg.py:586-592
+            if constexpr (Md::kFp64) {
+              sumQ[0] += q0_; sumQ[1] += q1_; sumQ[2] += q2_; sumQ[3] += q3_;
+              if (wasC) { sumQC[0] += q0_; sumQC[1] += q1_; sumQC[2] += q2_; sumQC[3] += q3_; }
+            } else {
+              const float m = wasC ? 1.0f : 0.0f;
+              tq[0] += q0_; tq[1] += q1_; tq[2] += q2_; tq[3] += q3_;
+              tqc[0] = fmaf(m, q0_, tqc[0]); tqc[1] = fmaf(m, q1_, tqc[1]);
+              tqc[2] = fmaf(m, q2_, tqc[2]); tqc[3] = fmaf(m, q3_, tqc[3]);
+            }
+          }
+
+          if (sel) {
+            int explore, rnd;
+            if constexpr (REPLAY) {
+              explore = a.u[site] < eps;  // algorithms.py:105
+              rnd = a.b[site];            // algorithms.py:108
+            } else {
+              explore = (w4[k4] >> 8) < thr;
+              rnd = (int)(w4[k4] & 1u);
+            }
+            const QT ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
+            const int greedy = (gb > ga) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
+            a_new = explore ? rnd : greedy;        // algorithms.py:109
+            n_sel_coop += (a_new == 0);
+            RT r_new;                              // spgg.py:321-323
+            if constexpr (kI8) {
+              int t = (int)r_old + (a_new == 0 ? rc.gain_i : -rc.loss_i);
+              t = max(t, rc.rmin_i);
+              t = min(t, rc.rmax_i);
+              r_new = (RT)t;
+            } else if constexpr (sizeof(RT) == 4) {
+              const float t = __fadd_rn(r_old, a_new == 0 ? rc.gainC_f : -rc.lossD_f);
+              r_new = fminf(fmaxf(t, rc.rmin_f), rc.rmax_f);
+            } else {
+              const double t = __dadd_rn(r_old, a_new == 0 ? rc.gainC : -rc.lossD);
+              r_new = fmin(fmax(t, rc.rmin), rc.rmax);
+            }
+            const int n5[5] = {sm_N[sidx], sm_N[sidx - SMW], sm_N[sidx + SMW], sm_N[sidx - 1],
+                               sm_N[sidx + 1]};
+            const Code cnew = pack_code<Md>(n5, Ccur, a_new ^ 1, s_new);
+            const long long pidx = (long long)(i + GH) * g.pitchB + col;
+            code_out[pidx] = cnew;
+            R_out[pidx] = r_new;
+            if (g.wrap_rows) {  // this handle owns every row: keep its own ghost rows current
+              if (i < GH) {
+                const long long gidx = (long long)(i + g.rows + GH) * g.pitchB + col;
+                code_out[gidx] = cnew;
+                R_out[gidx] = r_new;
+              }
+              if (i >= g.rows - GH) {
+                const long long gidx = (long long)(i - g.rows + GH) * g.pitchB + col;
+                code_out[gidx] = cnew;
+                R_out[gidx] = r_new;
+              }
+            }
+          }
+          if (upd) {
+            if constexpr (Md::kFp64) {
+              reinterpret_cast<double2 *>(Qp)[site * 2] = make_double2(q0_, q1_);
+              reinterpret_cast<double2 *>(Qp)[site * 2 + 1] = make_double2(q2_, q3_);
+            } else {
+              reinterpret_cast<float4 *>(Qp)[site] = make_float4(q0_, q1_, q2_, q3_);
+            }
+          }
+        }
+        if (sel) {
+          const uint32_t word = __ballot_sync(0xffffffffu, valid && a_new);
+          const int wi = (c0 >> 5) + k4;
+          if (lane == 0 && wi * 32 < g.L) {
+            S_out[(long long)(i + GH) * g.pitchW + wi] = word;
+            if (g.wrap_rows) {
+              if (i < GH) S_out[(long long)(i + g.rows + GH) * g.pitchW + wi] = word;
+              if (i >= g.rows - GH) S_out[(long long)(i - g.rows + GH) * g.pitchW + wi] = word;
+            }
+          }
+        }
+      }
+    }
+    // flush the per-tile packed counters
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+      cls_n[z] += (pk_n >> (8 * z)) & 0xffu;
+      cls_sn[z] += (pk_sn >> (16 * z)) & 0xffffull;
+      sumQ[z] += (double)tq[z];
+      sumQC[z] += (double)tqc[z];
+    }
+#pragma unroll
+    for (int z = 0; z < 6; ++z) grp[z] += (pk_grp >> (10 * z)) & 0x3ffull;
+    sumNI += (double)tni;
+    sumRatio += (double)tratio;
+    sumR += (double)tri + (double)trf;
+  }
+
+  // ---- per-CTA partial row, then the last CTA of the replica folds them in a fixed order
+  double v[NSTAT];
+#pragma unroll
+  for (int z = 0; z < NSTAT; ++z) v[z] = 0.0;
+  v[ST_NC_OLD] = (double)(cls_n[2] + cls_n[3]);
+  v[ST_N_CD] = (double)cls_n[2];
+  v[ST_N_DC] = (double)cls_n[1];
+  v[ST_NC_NEW] = (double)(cls_n[1] + cls_n[3]);
+  if constexpr (Md::kFp64) {
+    v[ST_SUM_P] = sumP; v[ST_SUM_P_C] = sumPC; v[ST_SUM_P_D] = sumPD; v[ST_SUM_WP_P] = sumWP;
+    v[ST_SUM_REW_C] = sumRewC; v[ST_SUM_REW_D] = sumRewD;
+  } else {
+#pragma unroll
+    for (int z = 0; z < 4; ++z) v[ST_X_SN0 + z] = (double)cls_sn[z];
+    // raw class counts ride in these four slots until the fold below
+    v[ST_SUM_P] = (double)cls_n[0]; v[ST_SUM_P_C] = (double)cls_n[1];
+    v[ST_SUM_P_D] = (double)cls_n[2]; v[ST_SUM_WP_P] = (double)cls_n[3];
+  }
+  v[ST_SUM_RATIO] = sumRatio;
+#pragma unroll
+  for (int z = 0; z < 6; ++z) v[ST_GROUP0 + z] = (double)grp[z];
+  v[ST_SUM_R] = sumR;
+#pragma unroll
+  for (int z = 0; z < 4; ++z) {
+    v[ST_SUM_Q + z] = sumQ[z];
+    v[ST_SUM_Q_C + z] = sumQC[z];
+  }
+  v[ST_SUM_NI] = sumNI;
+  v[ST_N_BEST_POS] = (double)n_best;
+  v[ST_N_BEST_2ND] = (double)n_best2;
+  v[ST_X_NSEL] = (double)n_sel_coop;
+  __syncthreads();
+  block_reduce<NSTAT>(v, sm_red);
+  double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
+  if (threadIdx.x < NSTAT) part[threadIdx.x] = sm_red[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicInc(a.tickets + rep, (unsigned)g.ctas_per_rep - 1u);
+    s_is_last = (t == (unsigned)g.ctas_per_rep - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  if (threadIdx.x < NSTAT) {
+    double x = 0.0;
+    const double *pp = a.partials + (long long)rep * g.ctas_per_rep * NSTAT + threadIdx.x;
+    for (int c = 0; c < g.ctas_per_rep; ++c) x += __ldcg(pp + (long long)c * NSTAT);
+    sm_red[threadIdx.x] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double *row = a.stats + ((long long)rep * a.cap + a.rel) * NSTAT;
+    double *s = sm_red;
+    if constexpr (kI8) s[ST_SUM_R] *= rc.rq;
+    if (upd) {
+      if constexpr (!Md::kFp64) {
+        // exact-count payoff sums per class: P = ((rc*SN/5 - 5*cost*C) - lo)/span
+        double Pc[4];
+        const double nc[4] = {s[ST_SUM_P], s[ST_SUM_P_C], s[ST_SUM_P_D], s[ST_SUM_WP_P]};
+        for (int z = 0; z < 4; ++z) {
+          const double C = (z >> 1) ? 1.0 : 0.0;
+          Pc[z] = ((rc.rc * s[ST_X_SN0 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) /
+                  rc.span;
+        }
+        s[ST_SUM_P] = Pc[0] + Pc[1] + Pc[2] + Pc[3];
+        s[ST_SUM_P_C] = Pc[2] + Pc[3];
+        s[ST_SUM_P_D] = Pc[0] + Pc[1];
+        s[ST_SUM_WP_P] = rc.wP * s[ST_SUM_P];
+        s[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
+        s[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
+      }
+      for (int z = 0; z < 4; ++z) s[ST_SUM_Q_D + z] = s[ST_SUM_Q + z] - s[ST_SUM_Q_C + z];
+      s[ST_GMAX] = (double)reinterpret_cast<const Val *>(a.gmax)[(long long)rep * a.cap + a.rel];
+      for (int z = 0; z < ST_X_SN0; ++z) row[z] = s[z];  // scratch columns stay zero
+    } else {
+      row[ST_SUM_R] = s[ST_SUM_R];
+    }
+    // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405).
+    // Only a handle that owns the whole lattice can tell; strips decide on the host.
+    if (sel && g.wrap_rows) {
+      const double nsel = s[ST_X_NSEL];
+      if (nsel == 0.0 || nsel == (double)g.site_stride) a.stop_at[rep] = a.j + 1;
+    }
+  }
+}
+
+// strip decomposition: boundary rows <-> contiguous halo buffers --------------------
+// buffer layout per replica: [GH rows of code][GH rows of R][GH rows of S bits]
+template <class Md>
+__global__ void k_halo_pack(Geom g, const void *code, const void *R, const uint32_t *S,
+                            unsigned char *to_up, unsigned char *to_down, long long rep_bytes) {
+  typedef typename Md::Code Code;
+  typedef typename Md::R RT;
+  const int rep = blockIdx.y;
+  const long long nB = (long long)GH * g.pitchB, nW = (long long)GH * g.pitchW;
+  const Code *cp = reinterpret_cast<const Code *>(code) + (long long)rep * g.plane_stride;
+  const RT *rp = reinterpret_cast<const RT *>(R) + (long long)rep * g.plane_stride;
+  const uint32_t *sp = S + (long long)rep * g.bits_stride;
+  unsigned char *up = to_up + rep * rep_bytes, *dn = to_down + rep * rep_bytes;
+  Code *upc = reinterpret_cast<Code *>(up), *dnc = reinterpret_cast<Code *>(dn);
+  RT *upr = reinterpret_cast<RT *>(up + sizeof(Code) * nB), *dnr = reinterpret_cast<RT *>(dn + sizeof(Code) * nB);
+  uint32_t *ups = reinterpret_cast<uint32_t *>(up + (sizeof(Code) + sizeof(RT)) * nB);
+  uint32_t *dns = reinterpret_cast<uint32_t *>(dn + (sizeof(Code) + sizeof(RT)) * nB);
+  const long long top = (long long)GH * g.pitchB, bot = (long long)g.rows * g.pitchB;  // first / last GH owned rows
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nB;
+       e += (long long)gridDim.x * blockDim.x) {
+    upc[e] = cp[top + e]; upr[e] = rp[top + e];
+    dnc[e] = cp[bot + e]; dnr[e] = rp[bot + e];
+  }
+  const long long topw = (long long)GH * g.pitchW, botw = (long long)g.rows * g.pitchW;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nW;
+       e += (long long)gridDim.x * blockDim.x) {
+    ups[e] = sp[topw + e];
+    dns[e] = sp[botw + e];
+  }
+}
+
+template <class Md>
+__global__ void k_halo_unpack(Geom g, void *code, void *R, uint32_t *S, const unsigned char *from_up,
+                              const unsigned char *from_down, long long rep_bytes) {
+  typedef typename Md::Code Code;
+  typedef typename Md::R RT;
+  const int rep = blockIdx.y;
+  const long long nB = (long long)GH * g.pitchB, nW = (long long)GH * g.pitchW;
+  Code *cp = reinterpret_cast<Code *>(code) + (long long)rep * g.plane_stride;
+  RT *rp = reinterpret_cast<RT *>(R) + (long long)rep * g.plane_stride;
+  uint32_t *sp = S + (long long)rep * g.bits_stride;
+  const unsigned char *up = from_up + rep * rep_bytes, *dn = from_down + rep * rep_bytes;
+  const Code *upc = reinterpret_cast<const Code *>(up), *dnc = reinterpret_cast<const Code *>(dn);
+  const RT *upr = reinterpret_cast<const RT *>(up + sizeof(Code) * nB);
+  const RT *dnr = reinterpret_cast<const RT *>(dn + sizeof(Code) * nB);
+  const uint32_t *ups = reinterpret_cast<const uint32_t *>(up + (sizeof(Code) + sizeof(RT)) * nB);
+  const uint32_t *dns = reinterpret_cast<const uint32_t *>(dn + (sizeof(Code) + sizeof(RT)) * nB);
+  // the upper neighbour's *last* rows become our top ghosts; the lower neighbour's first rows our bottom ghosts
+  const long long botg = (long long)(g.rows + GH) * g.pitchB;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nB;
+       e += (long long)gridDim.x * blockDim.x) {
+    cp[e] = upc[e]; rp[e] = upr[e];
+    cp[botg + e] = dnc[e]; rp[botg + e] = dnr[e];
+  }
+  const long long botgw = (long long)(g.rows + GH) * g.pitchW;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nW;
+       e += (long long)gridDim.x * blockDim.x) {
+    sp[e] = ups[e];
+    sp[botgw + e] = dns[e];
+  }
+}
+
+// device-side initial state with the reference ctor's distributions (spgg.py:121,129,162):
+// Q ~ U(-0.01, 0.01), R = 0, S ~ Bernoulli(1/2).  Philox counters use stream ids 1 (Q) and
+// 2 (S) in word 3 so they never collide with the per-iteration draws (stream 0).
+template <class Md>
+__global__ void k_init_random(Geom g, int rep, void *Q, void *R, uint32_t *S, uint32_t seed_lo,
+                              uint32_t seed_hi) {
+  typedef typename Md::Q QT;
+  typedef typename Md::R RT;
+  QT *Qp = reinterpret_cast<QT *>(Q) + (long long)rep * g.site_stride * 4;
+  RT *Rp = reinterpret_cast<RT *>(R) + (long long)rep * g.plane_stride;
+  uint32_t *Sp = S + (long long)rep * g.bits_stride;
+  const long long n_sites = g.site_stride;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n_sites;
+       x += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(x / g.L), j = (int)(x % g.L);
+    uint32_t w[4];
+    philox4x32_10((uint32_t)j, (uint32_t)(g.row0 + i), 0u, 1u, seed_lo, seed_hi, w);
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+      // 24-bit uniform in [0,1) -> [-0.01, 0.01)
+      const double uu = (double)(w[z] >> 8) * (1.0 / 16777216.0);
+      Qp[x * 4 + z] = (QT)(-0.01 + 0.02 * uu);
+    }
+  }
+  // planes incl. ghost rows: R = 0, S bits from stream 2 (ghost rows replicate periodic rows)
+  const long long n_words = (long long)(g.rows + 2 * GH) * g.pitchW;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_words;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int pr = (int)(e / g.pitchW), wi = (int)(e % g.pitchW);
+    int i = pr - GH;
+    uint32_t word = 0;
+    const bool ghost = (i < 0 || i >= g.rows);
+    if (ghost && g.wrap_rows) i = ((i % g.rows) + g.rows) % g.rows;
+    if ((!ghost || g.wrap_rows) && wi * 32 < g.L) {
+      uint32_t w[4];
+      philox4x32_10((uint32_t)(wi >> 2), (uint32_t)(g.row0 + i), 0u, 2u, seed_lo, seed_hi, w);
+      word = w[wi & 3];
+      const int rem = g.L - wi * 32;
+      if (rem < 32) word &= (1u << rem) - 1u;
+    }
+    Sp[e] = word;
+  }
+  const long long n_plane = (long long)(g.rows + 2 * GH) * g.pitchB;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_plane;
+       e += (long long)gridDim.x * blockDim.x)
+    Rp[e] = RT(0);
+}
+
+// host layout (reference arrays: _Sn bytes 0/1, R float64, q_table float64 (rows,L,2,2))
+// <-> device planes, `nrows` rows starting at local row i0.  One warp per 32-site word.
+// info[0] = error flag (1: S not 0/1, 2: R not representable in int8 units), info[1] = #cooperators
+template <class Md>
+__global__ void k_import_rows(Geom g, int rep, int i0, int nrows, const uint8_t *S, const double *R,
+                              const double *Q, void *Qd, void *Rd, uint32_t *Sd, double rq,
+                              unsigned long long *info) {
+  typedef typename Md::Q QT;
+  typedef typename Md::R RT;
+  QT *Qp = reinterpret_cast<QT *>(Qd) + (long long)rep * g.site_stride * 4;
+  RT *Rp = reinterpret_cast<RT *>(Rd) + (long long)rep * g.plane_stride;
+  uint32_t *Sp = Sd + (long long)rep * g.bits_stride;
+  const int lane = threadIdx.x & 31;
+  const int words = (g.L + 31) / 32;
+  const long long n_items = (long long)nrows * words;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long coop = 0;
+  for (long long it = warp0; it < n_items; it += n_warps) {
+    const int ii = (int)(it / words), w = (int)(it % words);
+    const int i = i0 + ii, col = w * 32 + lane;
+    const bool valid = col < g.L;
+    int bit = 0;
+    RT rv = RT(0);
+    if (valid) {
+      const long long src = (long long)ii * g.L + col;
+      const uint8_t sv = S[src];
+      if (sv > 1) atomicExch(info, 1ull);
+      bit = sv & 1;
+      const double r = R[src];
+      if constexpr (sizeof(RT) == 1) {
+        const double q = r / rq;
+        if (q != floor(q) || q < -128.0 || q > 127.0) atomicExch(info, 2ull);
+        rv = (RT)(int)q;
+      } else {
+        rv = (RT)r;
+      }
+      const long long site = (long long)i * g.L + col;
+#pragma unroll
+      for (int z = 0; z < 4; ++z) Qp[site * 4 + z] = (QT)Q[src * 4 + z];
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, valid && bit);
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) coop += __popc(vmask & ~word);
+    // physical rows receiving this row: itself + periodic ghost copies
+    int prs[3];
+    int np = 0;
+    prs[np++] = i + GH;
+    if (g.wrap_rows) {
+      if (i < GH) prs[np++] = i + g.rows + GH;
+      if (i >= g.rows - GH) prs[np++] = i - g.rows + GH;
+    }
+    for (int k = 0; k < np; ++k) {
+      if (valid) Rp[(long long)prs[k] * g.pitchB + col] = rv;
+      if (lane == 0) Sp[(long long)prs[k] * g.pitchW + w] = word;
+    }
+  }
+  if (lane == 0 && coop) atomicAdd(info + 1, coop);
+}
+
+template <class Md>
+__global__ void k_export_rows(Geom g, int rep, int i0, int nrows, uint8_t *S, double *R, double *Q,
+                              const void *Qd, const void *Rd, const uint32_t *Sd, double rq) {
+  typedef typename Md::Q QT;
+  typedef typename Md::R RT;
+  const QT *Qp = reinterpret_cast<const QT *>(Qd) + (long long)rep * g.site_stride * 4;
+  const RT *Rp = reinterpret_cast<const RT *>(Rd) + (long long)rep * g.plane_stride;
+  const uint32_t *Sp = Sd + (long long)rep * g.bits_stride;
+  const long long n = (long long)nrows * g.L;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int ii = (int)(e / g.L), col = (int)(e % g.L);
+    const int i = i0 + ii;
+    if (S) S[e] = (uint8_t)((Sp[(long long)(i + GH) * g.pitchW + (col >> 5)] >> (col & 31)) & 1u);
+    if (R) {
+      const RT rv = Rp[(long long)(i + GH) * g.pitchB + col];
+      R[e] = (sizeof(RT) == 1) ? (double)rv * rq : (double)rv;
+    }
+    if (Q) {
+      const long long site = (long long)i * g.L + col;
+#pragma unroll
+      for (int z = 0; z < 4; ++z) Q[e * 4 + z] = (double)Qp[site * 4 + z];
+    }
+  }
+}
+
+}  // namespace spgg
