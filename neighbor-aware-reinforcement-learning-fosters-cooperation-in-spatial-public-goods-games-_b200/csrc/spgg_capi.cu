@@ -3,11 +3,15 @@
 // computes needs a CUDA device and fails with SPGG_E_CUDA otherwise.
 #include "../../include/spgg.h"
 #include "spgg_kernels.cuh"
+#include "spgg_fast.cuh"
+
+#include <cudaTypedefs.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -68,6 +72,9 @@ struct spgg_handle {
   uint8_t *d_sc_S = nullptr;
   double *d_sc_R = nullptr, *d_sc_Q = nullptr;
   unsigned long long *d_sc_info = nullptr;
+  // fast path (spgg_fast.cuh): TMA descriptors of the two plane sets
+  bool fast = false;
+  FastMaps fmaps[2];  // [cur]: loads from plane set cur, stores into cur^1
   std::vector<double> eps_host;
   std::vector<uint32_t> thr_host;
   long long replay_first = 0, replay_n = 0;  // draws cover iterations replay_first+1 .. replay_first+replay_n
@@ -168,6 +175,38 @@ static size_t step_smem(int mode, int TR) {
   }
 }
 
+// ---------------------------------------------------------------- fast path plumbing
+typedef void (*fast_fn_t)(const FastMaps, KArgs);
+static fast_fn_t pick_fast(int M, int action) {
+  if (M == 2) return action ? k_step_fast<2, true> : k_step_fast<2, false>;
+  return action ? k_step_fast<1, true> : k_step_fast<1, false>;
+}
+static size_t fast_smem(int M) { return M == 2 ? FastSmem<2>::kTotal : FastSmem<1>::kTotal; }
+typedef void (*gfast_fn_t)(const CUtensorMap, GArgs);
+static gfast_fn_t pick_gfast(int M) { return M == 2 ? k_gmax_fast<2> : k_gmax_fast<1>; }
+static size_t gfast_smem(int M) { return M == 2 ? GmaxSmem<2>::kTotal : GmaxSmem<1>::kTotal; }
+
+static int make_map(CUtensorMap *map, void *base, uint64_t row_bytes, uint64_t n_rows, uint64_t n_rep,
+                    uint64_t rep_stride_bytes, uint32_t box_bytes, uint32_t box_rows) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SPGG_E_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  const cuuint64_t dims[3] = {row_bytes, n_rows, n_rep};
+  const cuuint64_t strides[2] = {row_bytes, rep_stride_bytes};
+  const cuuint32_t box[3] = {box_bytes, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SPGG_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SPGG_OK;
+}
+
 // ---------------------------------------------------------------- lifetime
 extern "C" int spgg_abi_version(void) { return SPGG_ABI_VERSION; }
 extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
@@ -237,10 +276,20 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
 
   Geom &g = h->g;
   g.L = p0.L; g.rows = p0.rows; g.row0 = p0.row0; g.wrap_rows = (p0.rows == p0.L);
-  g.pitchB = (p0.L + 15) / 16 * 16;
-  g.pitchW = ((p0.L + 31) / 32 + 3) / 4 * 4;
-  g.TR = g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4);
-  h->threads = 32 * std::min(8, g.TR);
+  g.pitchB = CPAD + (p0.L + 15) / 16 * 16 + CPAD;
+  g.pitchW = WPAD + ((p0.L + 31) / 32 + 3) / 4 * 4 + WPAD;
+  // fast path (spgg_fast.cuh): int8 throughput mode on 128-aligned lattices, |R| <= 15 units
+  {
+    const RepConst &r0 = h->rc_host[0];
+    bool ok = (h->mode == MODE_F32_I8) && (g.L % TC == 0) && (g.rows % FTR == 0) &&
+              getenv("SPGG_NO_FAST") == nullptr;
+    for (int r = 0; r < n_replicas && ok; ++r)
+      ok = h->rc_host[r].rmin_i >= -15 && h->rc_host[r].rmax_i <= 15;
+    (void)r0;
+    h->fast = ok;
+  }
+  g.TR = h->fast ? FTR : (g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4));
+  h->threads = h->fast ? FTHREADS : 32 * std::min(8, g.TR);
   g.n_tx = (g.L + TC - 1) / TC;
   g.n_ty = (g.rows + g.TR - 1) / g.TR;
   g.n_rep = n_replicas;
@@ -260,12 +309,20 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     if (!replay)
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, h->threads, h->smem_step));
   }
+  if (h->fast) {
+    fast_fn_t ff = pick_fast(h->M, h->action);
+    CUDA_TRY(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem(h->M)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff, FTHREADS, fast_smem(h->M)));
+    CUDA_TRY(cudaFuncSetAttribute(pick_gfast(h->M), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfast_smem(h->M)));
+  }
   CUDA_TRY(cudaFuncSetAttribute(pick_gmax(h->mode, h->M), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)h->smem_gmax));
   if (occ < 1) { delete h; return fail(SPGG_E_CUDA, "kernel does not fit on an SM (smem %zu)", h->smem_step); }
   const long long n_tiles = (long long)g.n_tx * g.n_ty;
   long long per_rep = std::max<long long>(1, ((long long)prop.multiProcessorCount * occ) / n_replicas);
   g.ctas_per_rep = (int)std::min<long long>(n_tiles, per_rep);
+  // the fast kernel's packed 16-bit counters bound the sites one thread may visit per launch
+  if (h->fast && (g.site_stride / ((long long)g.ctas_per_rep * FTHREADS)) > 60000) h->fast = false;
 
   const size_t nQ = (size_t)n_replicas * g.site_stride * 4 * h->elem_Q();
   const size_t nR = (size_t)n_replicas * g.plane_stride * h->elem_R();
@@ -287,6 +344,20 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   ALLOC(h->d_tickets, sizeof(unsigned) * n_replicas);
   ALLOC(h->d_stop, sizeof(int) * n_replicas);
 #undef ALLOC
+  if (h->fast) {
+    const int rowsCR = FTR + 2 * h->M, rowsS = FTR + 4;
+    const uint64_t nrows = (uint64_t)(g.rows + 2 * GH);
+    for (int i = 0; i < 2; ++i) {
+      FastMaps &fm = h->fmaps[i];
+      int e = make_map(&fm.ld_code, h->d_code[i], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, FROWB, rowsCR);
+      if (!e) e = make_map(&fm.ld_R, h->d_R[i], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, FROWB, rowsCR);
+      if (!e) e = make_map(&fm.ld_S, h->d_S[i], (uint64_t)g.pitchW * 4, nrows, n_replicas, (uint64_t)g.bits_stride * 4, FSROWB, rowsS);
+      if (!e) e = make_map(&fm.st_code, h->d_code[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
+      if (!e) e = make_map(&fm.st_R, h->d_R[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
+      if (!e) e = make_map(&fm.st_S, h->d_S[i ^ 1], (uint64_t)g.pitchW * 4, nrows, n_replicas, (uint64_t)g.bits_stride * 4, TC / 8, FTR);
+      if (e) { free_all(h); delete h; return e; }
+    }
+  }
   CUDA_TRY(cudaMemcpy(h->d_rc, h->rc_host.data(), sizeof(RepConst) * n_replicas, cudaMemcpyHostToDevice));
   std::vector<int> neg(n_replicas, -1);
   CUDA_TRY(cudaMemcpy(h->d_stop, neg.data(), sizeof(int) * n_replicas, cudaMemcpyHostToDevice));
@@ -539,8 +610,13 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   a.b = replay ? h->d_b + (size_t)draw * h->g.site_stride : nullptr;
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
-  step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
-  f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_step, st>>>(a);
+  if (h->fast && !replay) {
+    fast_fn_t ff = pick_fast(h->M, h->action);
+    ff<<<h->g.ctas_per_rep * h->n_rep, FTHREADS, fast_smem(h->M), st>>>(h->fmaps[h->cur], a);
+  } else {
+    step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
+    f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_step, st>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   if (do_select) h->cur ^= 1;
@@ -559,8 +635,12 @@ extern "C" int spgg_phase_gmax(spgg_t *h, void *stream_) {
   a.gmax = h->d_gmax;
   a.stop_at = h->d_stop;
   a.j = (int)(h->pend_t0 + h->pend_rel); a.rel = h->pend_rel; a.cap = h->cap;
-  gmax_fn_t f = pick_gmax(h->mode, h->M);
-  f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_gmax, st>>>(a);
+  if (h->fast) {
+    pick_gfast(h->M)<<<h->g.ctas_per_rep * h->n_rep, FTHREADS, gfast_smem(h->M), st>>>(h->fmaps[h->cur].ld_code, a);
+  } else {
+    gmax_fn_t f = pick_gmax(h->mode, h->M);
+    f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_gmax, st>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return SPGG_OK;

@@ -1,0 +1,590 @@
+// Fast path of the fused SPGG step for sm_100a: throughput mode (fp32 float4 Q, int8 R,
+// one-byte reward code, bit-packed strategies, Philox draws) on lattices whose side is a
+// multiple of 128.  Same arithmetic, bit for bit, as k_step<ModeF32I8,...> in
+// spgg_kernels.cuh (tests/test_gpu_parity.py::test_fast_path_equals_general_path); what
+// differs is how the work is laid out on the SM:
+//
+//   * the three halo'd tiles a CTA needs (reward codes, reputations, strategy bits) are
+//     staged by TMA 2-D tile loads (cp.async.bulk.tensor, one elected thread, mbarrier
+//     completion), double-buffered so the next tile lands while this one is computed; the
+//     lattices carry physical ghost rows/columns, so the boxes never wrap
+//   * the byte-valued stencils (cooperators per group N, their 5-group sum SigmaN, the
+//     reputation state) are computed 4 sites per 32-bit word with SWAR adds
+//   * Q goes HBM -> registers -> HBM as coalesced 16-byte accesses, four in flight per thread
+//   * statistics are exact packed integer counters plus fp32 partial sums per thread,
+//     folded in a fixed order (deterministic)
+//
+// Reference lines are cited at the arithmetic, as in spgg_kernels.cuh.
+#pragma once
+#include <cuda.h>
+
+#include "spgg_kernels.cuh"
+
+namespace spgg {
+
+constexpr int FTR = 16;            // tile rows
+constexpr int FROWB = 160;         // staged row bytes of code / R: 16 ghost + 128 + 16 ghost
+constexpr int FROWW = FROWB / 4;   // the same in 32-bit words
+constexpr int FSROWB = 48;         // staged row bytes of strategy bits: 16 + 16 + 16
+constexpr int FTHREADS = 256;
+
+template <int M>
+struct FastSmem {
+  static constexpr int kRowsCR = FTR + 2 * M;  // staged rows of code / R
+  static constexpr int kRowsS = FTR + 4;       // staged rows of strategy bits (halo 2)
+  static constexpr int kStageCode = 0;
+  static constexpr int kStageR = (kRowsCR * FROWB + 127) / 128 * 128;
+  static constexpr int kStageS = kStageR + (kRowsCR * FROWB + 127) / 128 * 128;
+  static constexpr int kStageBytes = kStageS + (kRowsS * FSROWB + 127) / 128 * 128;
+  static constexpr int kTxBytes = 2 * kRowsCR * FROWB + kRowsS * FSROWB;
+  // outputs of a tile, written back by TMA tile stores
+  static constexpr int kOutCode = 2 * kStageBytes;               // FTR x 128 bytes
+  static constexpr int kOutR = kOutCode + FTR * TC;
+  static constexpr int kOutS = kOutR + FTR * TC;                 // FTR x 16 bytes
+  // work planes, all with the staged row geometry (row r, word w <-> tile cols 4(w-4)..4(w-4)+3),
+  // one guard row before the first so flat stencils may read one word before a plane
+  static constexpr int kOffC = kOutS + 256 + FROWB;              // cooperator flags, rows -2..FTR+1
+  static constexpr int kOffN = kOffC + (FTR + 4) * FROWB;        // N, rows -1..FTR
+  static constexpr int kOffSN = kOffN + (FTR + 2) * FROWB;       // SigmaN, rows 0..FTR-1
+  static constexpr int kOffSt = kOffSN + FTR * FROWB;            // post-action state flags
+  static constexpr int kOffVal = kOffSt + FTR * FROWB;           // reward floats, rows -M..FTR+M-1
+  static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
+  static constexpr int kOffRed = kOffTab + 256 * 4;
+  static constexpr int kOffBar = kOffRed + 8 * NSTAT * 8;
+  static constexpr int kTotal = kOffBar + 64;
+};
+
+// ---- PTX helpers: mbarrier + TMA (Blackwell guide: TMA tile load with mbarrier signalling)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 28)) __trap();  // a lost TMA must not hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// bytes of the column-shifted neighbours of a 4-site word
+__device__ __forceinline__ uint32_t sh_l1(uint32_t prev, uint32_t cur) { return __byte_perm(prev, cur, 0x6543); }
+__device__ __forceinline__ uint32_t sh_r1(uint32_t cur, uint32_t next) { return __byte_perm(cur, next, 0x4321); }
+__device__ __forceinline__ uint32_t sh_2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
+
+struct FastMaps {
+  CUtensorMap ld_code, ld_R, ld_S;  // halo'd tile loads from the planes of iteration j
+  CUtensorMap st_code, st_R, st_S;  // tile stores into the planes of iteration j+1
+};
+
+template <int M, bool ACTION>
+__global__ void __launch_bounds__(FTHREADS, 3)
+k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
+  typedef FastSmem<M> SM;
+  constexpr int NK = (M == 2) ? 12 : 4;
+  const Geom &g = a.g;
+  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  const bool upd = a.do_update != 0;
+  const bool sel = (a.do_select != 0) && !(stop >= 0 && a.j == stop);
+
+  extern __shared__ __align__(128) unsigned char smem_fast[];
+  unsigned char *smem = smem_fast;
+  uint32_t *wC = reinterpret_cast<uint32_t *>(smem + SM::kOffC);
+  uint32_t *wN = reinterpret_cast<uint32_t *>(smem + SM::kOffN);
+  uint32_t *wSN = reinterpret_cast<uint32_t *>(smem + SM::kOffSN);
+  uint32_t *wSt = reinterpret_cast<uint32_t *>(smem + SM::kOffSt);
+  float *sm_val = reinterpret_cast<float *>(smem + SM::kOffVal);
+  float *sm_tab = reinterpret_cast<float *>(smem + SM::kOffTab);
+  float *sm_ratio = sm_tab + 128;
+  double *sm_red = reinterpret_cast<double *>(smem + SM::kOffRed);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kOffBar);
+  uint8_t *out_code = smem + SM::kOutCode;
+  int8_t *out_R = reinterpret_cast<int8_t *>(smem + SM::kOutR);
+  uint32_t *out_S = reinterpret_cast<uint32_t *>(smem + SM::kOutS);
+  __shared__ RepConst s_rc;
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < (int)(sizeof(RepConst) / 4); i += FTHREADS)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  for (int i = tid; i < 128; i += FTHREADS) {
+    sm_tab[i] = s_rc.rewtab[i];
+    sm_ratio[i] = s_rc.ratiotab[i];
+  }
+  const RepConst &rc = s_rc;
+
+  float4 *Qp = reinterpret_cast<float4 *>(a.Q) + (long long)rep * g.site_stride;
+
+  float inv_den = 0.f;
+  if (upd) {
+    const float gm = reinterpret_cast<const float *>(a.gmax)[(long long)rep * a.cap + a.rel];
+    inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));  // spgg.py:489 denominator
+  }
+  const uint32_t thr = sel ? a.thr_tab[(long long)(a.rel + 1) * g.n_rep + rep] : 0u;
+  const float alpha = rc.alpha_f, gamma = rc.gamma_f, kappa = rc.kappa_f;
+  const int gain_i = rc.gain_i, loss_i = rc.loss_i, rmin_i = rc.rmin_i, rmax_i = rc.rmax_i;
+  const bool has_ratio = rc.has_ratio != 0;
+  const uint32_t seed_lo = rc.seed_lo, seed_hi = rc.seed_hi;
+
+  // per-thread statistics: exact packed 16-bit counters + fp32 partial sums.
+  // class = C_old*2 + coop (spgg.py:383,419-420); pk_n01 holds classes 0 (low) and 1 (high), pk_n23 2 and 3
+  uint32_t pk_n01 = 0, pk_n23 = 0;
+  uint32_t pk_sn01 = 0, pk_sn23 = 0;              // sums of SigmaN per class (flushed every 32 tiles)
+  uint32_t pk_g01 = 0, pk_g23 = 0, pk_g45 = 0;    // group histogram, two 16-bit bins per word
+  uint32_t pk_best = 0;                           // low: #best>0, high: ... with a second-order arg-max
+  uint32_t n_sel = 0;
+  int sum_r = 0;
+  unsigned long long tot_sn[4] = {0, 0, 0, 0};
+  float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
+  float s_ni = 0.f, s_ratio = 0.f;
+
+  const int n_tiles = g.n_tx * g.n_ty;
+  auto issue = [&](int tile, int st) {
+    const int r0 = (tile / g.n_tx) * FTR, c0 = (tile % g.n_tx) * TC;
+    unsigned char *base = smem + st * SM::kStageBytes;
+    mbar_expect_tx(&bars[st], SM::kTxBytes);
+    tma_load_3d(base + SM::kStageCode, &tm.ld_code, &bars[st], c0, r0 + GH - M, rep);
+    tma_load_3d(base + SM::kStageR, &tm.ld_R, &bars[st], c0, r0 + GH - M, rep);
+    tma_load_3d(base + SM::kStageS, &tm.ld_S, &bars[st], c0 >> 3, r0 + GH - 2, rep);
+  };
+  if (tid == 0 && cta < n_tiles) issue(cta, 0);
+
+  int tiles_done = 0, stage = 0;
+  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
+    const int ty = tile / g.n_tx, tx = tile - ty * g.n_tx;
+    const int r0 = ty * FTR, c0 = tx * TC;
+    // prefetch the next tile into the other stage (its readers passed the barrier that
+    // closes the previous iteration)
+    if (tid == 0) {
+      if (tile + g.ctas_per_rep < n_tiles) issue(tile + g.ctas_per_rep, stage ^ 1);
+      if (sel) tma_store_wait_read();  // the previous tile's stores have left out_* 
+    }
+    mbar_wait(&bars[stage], (uint32_t)(tiles_done >> 1) & 1u);  // a stage completes once every 2 tiles
+    const unsigned char *st_base = smem + stage * SM::kStageBytes;
+    const uint32_t *st_code = reinterpret_cast<const uint32_t *>(st_base + SM::kStageCode);
+    const uint32_t *st_R = reinterpret_cast<const uint32_t *>(st_base + SM::kStageR);
+    const uint32_t *st_S = reinterpret_cast<const uint32_t *>(st_base + SM::kStageS);
+
+    // ---- phase A1: cooperator flags as bytes; one thread expands one staged bit word
+    // (32 sites) into 8 words of 4 flag bytes.  Rows -2..FTR+1, staged words 3..8.
+    if (tid < (FTR + 4) * 6) {
+      const int row = tid / 6, bw = tid - row * 6 + 3;
+      const uint32_t bits = ~st_S[row * (FSROWB / 4) + bw];  // 1 = cooperator
+      uint32_t *dst = wC + row * FROWW + (bw - 4) * 8 + 4;
+      if (bw == 3) {         // columns -4..-1 only
+        dst[7] = ((bits >> 28) * 0x00204081u) & 0x01010101u;
+      } else if (bw == 8) {  // columns 128..131 only
+        dst[0] = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+      } else {
+        uint4 lo, hi;
+        lo.x = (((bits >> 0) & 0xFu) * 0x00204081u) & 0x01010101u;
+        lo.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+        lo.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+        lo.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+        hi.x = (((bits >> 16) & 0xFu) * 0x00204081u) & 0x01010101u;
+        hi.y = (((bits >> 20) & 0xFu) * 0x00204081u) & 0x01010101u;
+        hi.z = (((bits >> 24) & 0xFu) * 0x00204081u) & 0x01010101u;
+        hi.w = ((bits >> 28) * 0x00204081u) & 0x01010101u;
+        *reinterpret_cast<uint4 *>(dst) = lo;
+        *reinterpret_cast<uint4 *>(dst + 4) = hi;
+      }
+    }
+    // ---- phase A2: reward of every staged code (flat over the staged plane, 4 codes per thread)
+    if (upd) {
+      for (int e = tid; e < SM::kRowsCR * FROWW; e += FTHREADS) {
+        const uint32_t cw = st_code[e];
+        float4 v;
+        v.x = sm_tab[(cw >> 1) & 0x7Fu];
+        v.y = sm_tab[(cw >> 9) & 0x7Fu];
+        v.z = sm_tab[(cw >> 17) & 0x7Fu];
+        v.w = sm_tab[(cw >> 25) & 0x7Fu];
+        *reinterpret_cast<float4 *>(sm_val + e * 4) = v;
+      }
+    }
+    // ---- phase A3: post-action reputation state (spgg.py:292-307) for the tile, 4 sites per
+    // word: v = R + 16 in each byte (|R| <= 15 is a launch precondition); sum v > 16 n <=> sum R > 0
+    if (!ACTION) {
+      for (int e = tid; e < FTR * 32; e += FTHREADS) {
+        const int row = e >> 5, w = (e & 31) + 4;
+        const uint32_t *rp = st_R + (row + M) * FROWW + w;
+        auto bias = [](uint32_t x) { return (x ^ 0x10101010u) & 0x1F1F1F1Fu; };
+        const uint32_t c = bias(rp[0]), l = bias(rp[-1]), r = bias(rp[1]);
+        const uint32_t u1 = bias(rp[-FROWW]), d1 = bias(rp[FROWW]);
+        uint32_t sumA = c + u1 + d1 + sh_l1(l, c) + sh_r1(c, r);
+        uint32_t flags;
+        if constexpr (M == 1) {
+          // 5 values in [1,31]: sum <= 155; sum > 80 <=> bit 7 of (sum + 47)
+          flags = ((sumA + 0x2F2F2F2Fu) >> 7) & 0x01010101u;
+        } else {
+          const uint32_t ul = bias(rp[-FROWW - 1]), ur = bias(rp[-FROWW + 1]);
+          const uint32_t dl = bias(rp[FROWW - 1]), dr = bias(rp[FROWW + 1]);
+          const uint32_t sumB = bias(rp[-2 * FROWW]) + bias(rp[2 * FROWW]) + sh_2(l, c) + sh_2(c, r) +
+                                sh_l1(ul, u1) + sh_r1(u1, ur) + sh_l1(dl, d1);
+          sumA += sh_r1(d1, dr);  // 6 values <= 186; sumB: 7 values <= 217
+          // 16-bit lanes: total > 16*13 = 208
+          const uint32_t lo = (sumA & 0x00FF00FFu) + (sumB & 0x00FF00FFu);
+          const uint32_t hi = ((sumA >> 8) & 0x00FF00FFu) + ((sumB >> 8) & 0x00FF00FFu);
+          const uint32_t flo = ((lo + (0x8000u - 209u) * 0x00010001u) >> 15) & 0x00010001u;
+          const uint32_t fhi = ((hi + (0x8000u - 209u) * 0x00010001u) >> 15) & 0x00010001u;
+          flags = flo | (fhi << 8);
+        }
+        wSt[row * FROWW + w] = flags;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: N = cooperators in the 5-site group centred on each site (spgg.py:23-36),
+    // flat over rows -1..FTR (words 0-2 / 37-39 of a row hold don't-care values)
+    for (int e = tid; e < (FTR + 2) * FROWW; e += FTHREADS) {
+      const uint32_t *cp = wC + FROWW + e;
+      const uint32_t c = cp[0];
+      wN[e] = c + cp[-FROWW] + cp[FROWW] + sh_l1(cp[-1], c) + sh_r1(c, cp[1]);
+    }
+    __syncthreads();
+    // ---- phase C: SigmaN = sum of N over the 5 groups a site belongs to (spgg.py:373-377)
+    for (int e = tid; e < FTR * FROWW; e += FTHREADS) {
+      const uint32_t *np_ = wN + FROWW + e;
+      const uint32_t c = np_[0];
+      wSN[e] = c + np_[-FROWW] + np_[FROWW] + sh_l1(np_[-1], c) + sh_r1(c, np_[1]);
+    }
+    __syncthreads();
+
+    // ---- main phase: warp = one 128-site row segment, lane = 4 sites strided by 32
+    const uint8_t *bC = reinterpret_cast<const uint8_t *>(wC);
+    const uint8_t *bN = reinterpret_cast<const uint8_t *>(wN);
+    const uint8_t *bSN = reinterpret_cast<const uint8_t *>(wSN);
+    const uint8_t *bSt = reinterpret_cast<const uint8_t *>(wSt);
+    const uint8_t *bCode = reinterpret_cast<const uint8_t *>(st_code);
+    const int8_t *bR = reinterpret_cast<const int8_t *>(st_R);
+    float4 *qtile = Qp + ((long long)r0 * g.L + c0 + lane);
+#pragma unroll 1
+    for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
+      float4 *qrow = qtile + (long long)rr * g.L;
+      float4 qn = __ldcs(qrow);
+      uint32_t w4[4] = {0, 0, 0, 0};
+      if (sel) {
+        // counter = (column group, global row, iteration, 0); one call -> 4 sites
+        philox4x32_10((uint32_t)(((c0 >> 7) << 5) | lane), (uint32_t)(g.row0 + r0 + rr),
+                      (uint32_t)(a.j + 1), 0u, seed_lo, seed_hi, w4);
+      }
+      const int rb = rr * FROWB + CPAD + lane;  // byte offset of (rr, lane) in a tile-row-indexed plane
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int bo = rb + 32 * k4;
+        float q0_ = qn.x, q1_ = qn.y, q2_ = qn.z, q3_ = qn.w;
+        if (k4 < 3) qn = __ldcs(qrow + 32 * (k4 + 1));
+        const int r_old = bR[bo + M * FROWB];
+        const int Ccur = bC[bo + 2 * FROWB];
+        const int s_new = ACTION ? Ccur : (int)bSt[bo];
+        sum_r += r_old;
+        if (upd) {
+          const int crow = bo + M * FROWB;
+          const uint32_t code = bCode[crow];
+          const int s = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
+          const float vx = sm_val[crow];
+          // neighbour-aware term inputs: spgg.py:486-494 (first arg-max wins)
+          float best = 0.f;
+          int bidx = crow;
+          bool second = false;
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            const int nidx = crow - c_off[k][0] * FROWB - c_off[k][1];
+            const float d = __fsub_rn(sm_val[nidx], vx);
+            if (k == 0 || d > best) { best = d; bidx = nidx; second = (k >= 4); }
+          }
+          const bool same = (((bCode[bidx] >> 1) & 1u) == (unsigned)coop);
+          const int ee = 2 * s + (coop ^ 1);  // index of Q[s][a], a = !coop
+          const float qe = sel4<float>(ee, q0_, q1_, q2_, q3_);
+          const float na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
+          const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na, nb), vx), qe);  // algorithms.py:128
+          const float qtd = __fmaf_rn(alpha, td, qe);                           // algorithms.py:131
+          const float lam = __fmul_rn(__fmul_rn(kappa, fmaxf(0.0f, best)), inv_den);  // spgg.py:489
+          const float nu = same ? lam : -lam;                                   // spgg.py:494-495
+          // TD error on the table after the TD write (spgg.py:446-473), for the NI statistic
+          const bool hit = (s_new == s);
+          const float na2 = (hit && coop) ? qtd : na;
+          const float nb2 = (hit && !coop) ? qtd : nb;
+          const float td2 = __fsub_rn(__fmaf_rn(gamma, fmaxf(na2, nb2), vx), qtd);
+          const float qfin = __fadd_rn(qtd, nu);                                // spgg.py:509
+          const float an = fabsf(nu);
+          s_ni += __fdividef(an, fabsf(alpha * td2) + an + 1e-8f);              // x100 at the fold; spgg.py:512
+          q0_ = (ee == 0) ? qfin : q0_;
+          q1_ = (ee == 1) ? qfin : q1_;
+          q2_ = (ee == 2) ? qfin : q2_;
+          q3_ = (ee == 3) ? qfin : q3_;
+          const uint32_t inc = 1u << (coop << 4);
+          const uint32_t snv = (code >> 3) << (coop << 4);
+          if (wasC) { pk_n23 += inc; pk_sn23 += snv; } else { pk_n01 += inc; pk_sn01 += snv; }
+          if (has_ratio && coop) s_ratio += sm_ratio[code >> 1];
+          if (best > 0.f) pk_best += second ? 0x10001u : 1u;
+          const int nd = 5 - (int)bN[bo + FROWB];                               // spgg.py:586-592
+          const uint32_t gone = 1u << ((nd & 1) << 4);
+          if (nd < 2) pk_g01 += gone; else if (nd < 4) pk_g23 += gone; else pk_g45 += gone;
+          const float m = wasC ? 1.0f : 0.0f;
+          sq0 += q0_; sq1 += q1_; sq2 += q2_; sq3 += q3_;
+          sc0 = fmaf(m, q0_, sc0); sc1 = fmaf(m, q1_, sc1); sc2 = fmaf(m, q2_, sc2); sc3 = fmaf(m, q3_, sc3);
+          __stcs(qrow + 32 * k4, make_float4(q0_, q1_, q2_, q3_));
+        }
+        if (sel) {
+          const bool explore = (w4[k4] >> 8) < thr;
+          const int rnd = (int)(w4[k4] & 1u);
+          const float ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
+          const int greedy = (gb > ga) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
+          const int a_new = explore ? rnd : greedy;  // algorithms.py:109
+          n_sel += (a_new ^ 1);
+          int t = r_old + (a_new == 0 ? gain_i : -loss_i);  // spgg.py:321-323
+          t = min(max(t, rmin_i), rmax_i);
+          const uint32_t cnew = ((uint32_t)bSN[bo] << 3) | (Ccur << 2) | ((a_new ^ 1) << 1) | s_new;
+          const int oo = rr * TC + lane + 32 * k4;
+          out_code[oo] = (uint8_t)cnew;
+          out_R[oo] = (int8_t)t;
+          const uint32_t word = __ballot_sync(0xffffffffu, a_new);
+          if (lane == 0) out_S[rr * 4 + k4] = word;
+        }
+      }
+    }
+    // 16-bit fields: SigmaN <= 25 per site, <= 8 sites per tile and thread
+    if ((tiles_done & 31) == 31) {
+      tot_sn[0] += pk_sn01 & 0xffffu; tot_sn[1] += pk_sn01 >> 16;
+      tot_sn[2] += pk_sn23 & 0xffffu; tot_sn[3] += pk_sn23 >> 16;
+      pk_sn01 = pk_sn23 = 0;
+    }
+    if (sel) fence_proxy_async();  // make out_* visible to the TMA engine
+    __syncthreads();               // everyone is done with this stage, the work planes and out_*
+    if (sel) {
+      if (tid == 0) {
+        tma_store_3d(&tm.st_code, out_code, CPAD + c0, r0 + GH, rep);
+        tma_store_3d(&tm.st_R, out_R, CPAD + c0, r0 + GH, rep);
+        tma_store_3d(&tm.st_S, out_S, (WPAD * 4) + (c0 >> 3), r0 + GH, rep);
+        tma_store_commit();
+      }
+      // periodic copies other tiles read: ghost columns / ghost rows, edge tiles only
+      const bool edge = tx == 0 || tx == g.n_tx - 1 || (g.wrap_rows && (ty == 0 || ty == g.n_ty - 1));
+      if (edge) {
+        uint8_t *code_out = reinterpret_cast<uint8_t *>(a.code_out) + (long long)rep * g.plane_stride;
+        int8_t *R_out = reinterpret_cast<int8_t *>(a.R_out) + (long long)rep * g.plane_stride;
+        uint32_t *S_out = a.S_out + (long long)rep * g.bits_stride;
+        for (int e = tid; e < FTR * TC; e += FTHREADS) {
+          const int rr = e >> 7, cc = e & (TC - 1);
+          const int i = r0 + rr, col = c0 + cc;
+          const bool ec = col < GC || col >= g.L - GC;
+          const bool er = g.wrap_rows && (i < GH || i >= g.rows - GH);
+          if (ec || er) {
+            store_cell<uint8_t>(code_out, g, i, col, out_code[e]);
+            store_cell<int8_t>(R_out, g, i, col, out_R[e]);
+          }
+        }
+        for (int e = tid; e < FTR * 4; e += FTHREADS) {
+          const int rr = e >> 2, wi = (c0 >> 5) + (e & 3);
+          store_bits_word(S_out, g, r0 + rr, wi, out_S[e]);
+        }
+        __syncthreads();  // out_* is read above; the next tile overwrites it
+      }
+    }
+  }
+  tot_sn[0] += pk_sn01 & 0xffffu; tot_sn[1] += pk_sn01 >> 16;
+  tot_sn[2] += pk_sn23 & 0xffffu; tot_sn[3] += pk_sn23 >> 16;
+  if (tid == 0 && sel) tma_store_wait_all();
+
+  // ---- per-CTA partial row, then the last CTA of the replica folds them in a fixed order
+  double v[NSTAT];
+#pragma unroll
+  for (int z = 0; z < NSTAT; ++z) v[z] = 0.0;
+  const double n0 = (double)(pk_n01 & 0xffffu), n1 = (double)(pk_n01 >> 16);
+  const double n2 = (double)(pk_n23 & 0xffffu), n3 = (double)(pk_n23 >> 16);
+  v[ST_NC_OLD] = n2 + n3; v[ST_N_CD] = n2; v[ST_N_DC] = n1; v[ST_NC_NEW] = n1 + n3;
+  v[ST_SUM_P] = n0; v[ST_SUM_P_C] = n1; v[ST_SUM_P_D] = n2; v[ST_SUM_WP_P] = n3;  // raw class counts until the fold
+#pragma unroll
+  for (int z = 0; z < 4; ++z) v[ST_X_SN0 + z] = (double)tot_sn[z];
+  v[ST_SUM_RATIO] = (double)s_ratio;
+  v[ST_GROUP0 + 0] = (double)(pk_g01 & 0xffffu); v[ST_GROUP0 + 1] = (double)(pk_g01 >> 16);
+  v[ST_GROUP0 + 2] = (double)(pk_g23 & 0xffffu); v[ST_GROUP0 + 3] = (double)(pk_g23 >> 16);
+  v[ST_GROUP0 + 4] = (double)(pk_g45 & 0xffffu); v[ST_GROUP0 + 5] = (double)(pk_g45 >> 16);
+  v[ST_SUM_R] = (double)sum_r;
+  v[ST_SUM_Q + 0] = (double)sq0; v[ST_SUM_Q + 1] = (double)sq1; v[ST_SUM_Q + 2] = (double)sq2; v[ST_SUM_Q + 3] = (double)sq3;
+  v[ST_SUM_Q_C + 0] = (double)sc0; v[ST_SUM_Q_C + 1] = (double)sc1; v[ST_SUM_Q_C + 2] = (double)sc2; v[ST_SUM_Q_C + 3] = (double)sc3;
+  v[ST_SUM_NI] = (double)s_ni * 100.0;
+  v[ST_N_BEST_POS] = (double)(pk_best & 0xffffu);
+  v[ST_N_BEST_2ND] = (double)(pk_best >> 16);
+  v[ST_X_NSEL] = (double)n_sel;
+  __syncthreads();
+  block_reduce<NSTAT>(v, sm_red);
+  double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
+  if (tid < NSTAT) part[tid] = sm_red[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicInc(a.tickets + rep, (unsigned)g.ctas_per_rep - 1u);
+    s_is_last = (t == (unsigned)g.ctas_per_rep - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  if (tid < NSTAT) {
+    double x = 0.0;
+    const double *pp = a.partials + (long long)rep * g.ctas_per_rep * NSTAT + tid;
+    for (int c = 0; c < g.ctas_per_rep; ++c) x += __ldcg(pp + (long long)c * NSTAT);
+    sm_red[tid] = x;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double *row = a.stats + ((long long)rep * a.cap + a.rel) * NSTAT;
+    double *s = sm_red;
+    s[ST_SUM_R] *= rc.rq;
+    if (upd) {
+      // exact-count payoff sums per class: P = ((rc*SN/5 - 5*cost*C) - lo)/span
+      double Pc[4];
+      const double nc[4] = {s[ST_SUM_P], s[ST_SUM_P_C], s[ST_SUM_P_D], s[ST_SUM_WP_P]};
+      for (int z = 0; z < 4; ++z) {
+        const double C = (z >> 1) ? 1.0 : 0.0;
+        Pc[z] = ((rc.rc * s[ST_X_SN0 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) / rc.span;
+      }
+      s[ST_SUM_P] = Pc[0] + Pc[1] + Pc[2] + Pc[3];
+      s[ST_SUM_P_C] = Pc[2] + Pc[3];
+      s[ST_SUM_P_D] = Pc[0] + Pc[1];
+      s[ST_SUM_WP_P] = rc.wP * s[ST_SUM_P];
+      s[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
+      s[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
+      for (int z = 0; z < 4; ++z) s[ST_SUM_Q_D + z] = s[ST_SUM_Q + z] - s[ST_SUM_Q_C + z];
+      s[ST_GMAX] = (double)reinterpret_cast<const float *>(a.gmax)[(long long)rep * a.cap + a.rel];
+      for (int z = 0; z < ST_X_SN0; ++z) row[z] = s[z];
+    } else {
+      row[ST_SUM_R] = s[ST_SUM_R];
+    }
+    if (sel && g.wrap_rows) {  // uniform lattice after this action -> next iteration breaks (spgg.py:405)
+      const double nsel = s[ST_X_NSEL];
+      if (nsel == 0.0 || nsel == (double)g.site_stride) a.stop_at[rep] = a.j + 1;
+    }
+  }
+}
+
+// lattice-global max |reward difference| of iteration j (spgg.py:486-488), fast path: the code
+// tile + halo is staged by TMA, rewards are looked up 4 codes per thread, and every unordered
+// neighbour pair is visited once (the offset set is symmetric, |d| too).
+template <int M>
+struct GmaxSmem {
+  static constexpr int kRowsCR = FTR + 2 * M;
+  static constexpr int kStageBytes = (kRowsCR * FROWB + 127) / 128 * 128;
+  static constexpr int kOffVal = 2 * kStageBytes;
+  static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
+  static constexpr int kOffBar = kOffTab + 128 * 4;
+  static constexpr int kTotal = kOffBar + 64;
+};
+
+template <int M>
+__global__ void __launch_bounds__(FTHREADS, 4)
+k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
+  typedef GmaxSmem<M> SM;
+  const Geom &g = a.g;
+  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  extern __shared__ __align__(128) unsigned char smem_gfast[];
+  unsigned char *smem = smem_gfast;
+  float *sm_val = reinterpret_cast<float *>(smem + SM::kOffVal);
+  float *sm_tab = reinterpret_cast<float *>(smem + SM::kOffTab);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kOffBar);
+  __shared__ float s_wmax[FTHREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 128) sm_tab[tid] = a.rc[rep].rewtab[tid];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int n_tiles = g.n_tx * g.n_ty;
+  auto issue = [&](int tile, int st) {
+    const int r0 = (tile / g.n_tx) * FTR, c0 = (tile % g.n_tx) * TC;
+    mbar_expect_tx(&bars[st], SM::kRowsCR * FROWB);
+    tma_load_3d(smem + st * SM::kStageBytes, &ld_code, &bars[st], c0, r0 + GH - M, rep);
+  };
+  if (tid == 0 && cta < n_tiles) issue(cta, 0);
+  float lmax = 0.f;
+  int tiles_done = 0, stage = 0;
+  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
+    if (tid == 0 && tile + g.ctas_per_rep < n_tiles) issue(tile + g.ctas_per_rep, stage ^ 1);
+    mbar_wait(&bars[stage], (uint32_t)(tiles_done >> 1) & 1u);
+    const uint32_t *st_code = reinterpret_cast<const uint32_t *>(smem + stage * SM::kStageBytes);
+    for (int e = tid; e < SM::kRowsCR * FROWW; e += FTHREADS) {
+      const uint32_t cw = st_code[e];
+      float4 v;
+      v.x = sm_tab[(cw >> 1) & 0x7Fu];
+      v.y = sm_tab[(cw >> 9) & 0x7Fu];
+      v.z = sm_tab[(cw >> 17) & 0x7Fu];
+      v.w = sm_tab[(cw >> 25) & 0x7Fu];
+      *reinterpret_cast<float4 *>(sm_val + e * 4) = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
+      const int rb = (rr + M) * FROWB + CPAD + lane;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int crow = rb + 32 * k4;
+        const float vx = sm_val[crow];
+        // one representative of every +/- offset pair: (1,0) (0,1) | (2,0) (0,2) (1,1) (1,-1)
+        lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - FROWB], vx)));
+        lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - 1], vx)));
+        if constexpr (M == 2) {
+          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - 2 * FROWB], vx)));
+          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - 2], vx)));
+          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - FROWB - 1], vx)));
+          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - FROWB + 1], vx)));
+        }
+      }
+    }
+    __syncthreads();  // the value plane and this stage are free again
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_down_sync(0xffffffffu, lmax, o));
+  if (lane == 0) s_wmax[warp] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_wmax[0];
+    for (int w = 1; w < FTHREADS / 32; ++w) m = fmaxf(m, s_wmax[w]);
+    // non-negative IEEE floats order like unsigned integers
+    atomicMax(reinterpret_cast<unsigned int *>(a.gmax) + (long long)rep * a.cap + a.rel, __float_as_uint(m));
+  }
+}
+
+}  // namespace spgg

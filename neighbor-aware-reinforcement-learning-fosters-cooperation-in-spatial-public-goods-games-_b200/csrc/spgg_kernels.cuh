@@ -22,6 +22,9 @@
 namespace spgg {
 
 constexpr int GH = 2;            // ghost rows on each side of every lattice plane
+constexpr int CPAD = 16;         // ghost columns (elements) on each side of the code / R planes
+constexpr int WPAD = 4;          // ghost words on each side of a strategy bit row
+constexpr int GC = 2;            // ghost columns actually kept current (>= max halo)
 constexpr int TC = 128;          // tile columns: one warp covers a 128-site row segment
 constexpr int HP = 4;            // smem column pad on each side (>= widest halo)
 constexpr int SMW = TC + 2 * HP; // smem row stride (elements)
@@ -65,8 +68,8 @@ struct RepConst {
 
 struct Geom {
   int L, rows, row0, wrap_rows;
-  int pitchB;   // elements per row of the byte planes (code, R)
-  int pitchW;   // 32-bit words per row of the strategy bit plane
+  int pitchB;   // elements per row of the code / R planes: CPAD + roundup(L,16) + CPAD
+  int pitchW;   // 32-bit words per row of the strategy bit plane: WPAD + roundup(words,4) + WPAD
   int n_tx, n_ty, TR;
   int ctas_per_rep, n_rep;
   long long plane_stride; // elements per replica, (rows+2GH)*pitchB
@@ -226,7 +229,7 @@ __device__ __forceinline__ void load_tile(T *sm, const T *plane, const Geom &g, 
     T v = T(0);
     if (prow >= 0 && prow < g.rows + 2 * GH) {
       const int col = wrap_col(c0 + cc, g.L);
-      v = plane[(long long)prow * g.pitchB + col];
+      v = plane[(long long)prow * g.pitchB + CPAD + col];
     }
     sm[(rr + HR) * SMW + cc + HP] = v;
   }
@@ -243,7 +246,7 @@ __device__ __forceinline__ void load_coop_tile(uint8_t *sm, const uint32_t *bits
     uint8_t v = 0;
     if (prow >= 0 && prow < g.rows + 2 * GH) {
       const int col = wrap_col(c0 + cc, g.L);
-      const uint32_t w = bits[(long long)prow * g.pitchW + (col >> 5)];
+      const uint32_t w = bits[(long long)prow * g.pitchW + WPAD + (col >> 5)];
       v = (uint8_t)(((w >> (col & 31)) & 1u) ^ 1u);
     }
     sm[(rr + HR) * SMW + cc + HP] = v;
@@ -271,6 +274,57 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *sm_red /* 
 }
 
 __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+
+// ------------------------------------------------------------------ plane stores
+// A value of site (i, col) goes to its own cell plus the periodic copies other tiles read:
+// ghost columns (always) and ghost rows (when this handle owns every row).
+template <class T>
+__device__ __forceinline__ void store_cell(T *plane, const Geom &g, int i, int col, T v) {
+  int gcol = -1;
+  if (col < GC) gcol = CPAD + g.L + col;
+  else if (col >= g.L - GC) gcol = CPAD + col - g.L;
+  long long rowoff = (long long)(i + GH) * g.pitchB;
+  plane[rowoff + CPAD + col] = v;
+  if (gcol >= 0) plane[rowoff + gcol] = v;
+  if (g.wrap_rows) {
+    if (i < GH) {
+      rowoff = (long long)(i + g.rows + GH) * g.pitchB;
+      plane[rowoff + CPAD + col] = v;
+      if (gcol >= 0) plane[rowoff + gcol] = v;
+    }
+    if (i >= g.rows - GH) {
+      rowoff = (long long)(i - g.rows + GH) * g.pitchB;
+      plane[rowoff + CPAD + col] = v;
+      if (gcol >= 0) plane[rowoff + gcol] = v;
+    }
+  }
+}
+// strategy word wi of row i (ghost words only exist when L is a multiple of 32)
+__device__ __forceinline__ void store_bits_word(uint32_t *S, const Geom &g, int i, int wi, uint32_t word) {
+  const int nW = (g.L + 31) >> 5;
+  const bool gw = (g.L & 31) == 0;
+  const int gl = (gw && wi == nW - 1) ? WPAD - 1 : -1;  // left ghost word <- last data word
+  const int gr = (gw && wi == 0) ? WPAD + nW : -1;      // right ghost word <- first data word
+  long long rowoff = (long long)(i + GH) * g.pitchW;
+  S[rowoff + WPAD + wi] = word;
+  if (gl >= 0) S[rowoff + gl] = word;
+  if (gr >= 0) S[rowoff + gr] = word;
+  if (g.wrap_rows) {
+    if (i < GH) {
+      rowoff = (long long)(i + g.rows + GH) * g.pitchW;
+      S[rowoff + WPAD + wi] = word;
+      if (gl >= 0) S[rowoff + gl] = word;
+      if (gr >= 0) S[rowoff + gr] = word;
+    }
+    if (i >= g.rows - GH) {
+      rowoff = (long long)(i - g.rows + GH) * g.pitchW;
+      S[rowoff + WPAD + wi] = word;
+      if (gl >= 0) S[rowoff + gl] = word;
+      if (gr >= 0) S[rowoff + gr] = word;
+    }
+  }
+}
 
 // =================================================================== k_gmax
 struct GArgs {
@@ -319,7 +373,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
         Val v = Val(0);
         if (prow >= 0 && prow < g.rows + 2 * GH) {
           const int col = wrap_col(c0 + cc, g.L);
-          v = val_of_code<Md>(code_in[(long long)prow * g.pitchB + col], s_rc, sm_tab);
+          v = val_of_code<Md>(code_in[(long long)prow * g.pitchB + CPAD + col], s_rc, sm_tab);
         }
         sm_val[(rr + HR) * SMW + cc + HP] = v;
       }
@@ -642,21 +696,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
             const int n5[5] = {sm_N[sidx], sm_N[sidx - SMW], sm_N[sidx + SMW], sm_N[sidx - 1],
                                sm_N[sidx + 1]};
             const Code cnew = pack_code<Md>(n5, Ccur, a_new ^ 1, s_new);
-            const long long pidx = (long long)(i + GH) * g.pitchB + col;
-            code_out[pidx] = cnew;
-            R_out[pidx] = r_new;
-            if (g.wrap_rows) {  // this handle owns every row: keep its own ghost rows current
-              if (i < GH) {
-                const long long gidx = (long long)(i + g.rows + GH) * g.pitchB + col;
-                code_out[gidx] = cnew;
-                R_out[gidx] = r_new;
-              }
-              if (i >= g.rows - GH) {
-                const long long gidx = (long long)(i - g.rows + GH) * g.pitchB + col;
-                code_out[gidx] = cnew;
-                R_out[gidx] = r_new;
-              }
-            }
+            store_cell<Code>(code_out, g, i, col, cnew);
+            store_cell<RT>(R_out, g, i, col, r_new);
           }
           if (upd) {
             if constexpr (Md::kFp64) {
@@ -670,13 +711,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
         if (sel) {
           const uint32_t word = __ballot_sync(0xffffffffu, valid && a_new);
           const int wi = (c0 >> 5) + k4;
-          if (lane == 0 && wi * 32 < g.L) {
-            S_out[(long long)(i + GH) * g.pitchW + wi] = word;
-            if (g.wrap_rows) {
-              if (i < GH) S_out[(long long)(i + g.rows + GH) * g.pitchW + wi] = word;
-              if (i >= g.rows - GH) S_out[(long long)(i - g.rows + GH) * g.pitchW + wi] = word;
-            }
-          }
+          if (lane == 0 && wi * 32 < g.L) store_bits_word(S_out, g, i, wi, word);
         }
       }
     }
@@ -868,23 +903,18 @@ __global__ void k_init_random(Geom g, int rep, void *Q, void *R, uint32_t *S, ui
       Qp[x * 4 + z] = (QT)(-0.01 + 0.02 * uu);
     }
   }
-  // planes incl. ghost rows: R = 0, S bits from stream 2 (ghost rows replicate periodic rows)
-  const long long n_words = (long long)(g.rows + 2 * GH) * g.pitchW;
+  // strategy bits from stream 2, written through the ghost-aware store; R planes are zero
+  const int nW = (g.L + 31) >> 5;
+  const long long n_words = (long long)g.rows * nW;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_words;
        e += (long long)gridDim.x * blockDim.x) {
-    const int pr = (int)(e / g.pitchW), wi = (int)(e % g.pitchW);
-    int i = pr - GH;
-    uint32_t word = 0;
-    const bool ghost = (i < 0 || i >= g.rows);
-    if (ghost && g.wrap_rows) i = ((i % g.rows) + g.rows) % g.rows;
-    if ((!ghost || g.wrap_rows) && wi * 32 < g.L) {
-      uint32_t w[4];
-      philox4x32_10((uint32_t)(wi >> 2), (uint32_t)(g.row0 + i), 0u, 2u, seed_lo, seed_hi, w);
-      word = w[wi & 3];
-      const int rem = g.L - wi * 32;
-      if (rem < 32) word &= (1u << rem) - 1u;
-    }
-    Sp[e] = word;
+    const int i = (int)(e / nW), wi = (int)(e % nW);
+    uint32_t w[4];
+    philox4x32_10((uint32_t)(wi >> 2), (uint32_t)(g.row0 + i), 0u, 2u, seed_lo, seed_hi, w);
+    uint32_t word = w[wi & 3];
+    const int rem = g.L - wi * 32;
+    if (rem < 32) word &= (1u << rem) - 1u;
+    store_bits_word(Sp, g, i, wi, word);
   }
   const long long n_plane = (long long)(g.rows + 2 * GH) * g.pitchB;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_plane;
@@ -936,18 +966,8 @@ __global__ void k_import_rows(Geom g, int rep, int i0, int nrows, const uint8_t 
     const uint32_t word = __ballot_sync(0xffffffffu, valid && bit);
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
     if (lane == 0) coop += __popc(vmask & ~word);
-    // physical rows receiving this row: itself + periodic ghost copies
-    int prs[3];
-    int np = 0;
-    prs[np++] = i + GH;
-    if (g.wrap_rows) {
-      if (i < GH) prs[np++] = i + g.rows + GH;
-      if (i >= g.rows - GH) prs[np++] = i - g.rows + GH;
-    }
-    for (int k = 0; k < np; ++k) {
-      if (valid) Rp[(long long)prs[k] * g.pitchB + col] = rv;
-      if (lane == 0) Sp[(long long)prs[k] * g.pitchW + w] = word;
-    }
+    if (valid) store_cell<RT>(Rp, g, i, col, rv);
+    if (lane == 0) store_bits_word(Sp, g, i, w, word);
   }
   if (lane == 0 && coop) atomicAdd(info + 1, coop);
 }
@@ -965,9 +985,9 @@ __global__ void k_export_rows(Geom g, int rep, int i0, int nrows, uint8_t *S, do
        e += (long long)gridDim.x * blockDim.x) {
     const int ii = (int)(e / g.L), col = (int)(e % g.L);
     const int i = i0 + ii;
-    if (S) S[e] = (uint8_t)((Sp[(long long)(i + GH) * g.pitchW + (col >> 5)] >> (col & 31)) & 1u);
+    if (S) S[e] = (uint8_t)((Sp[(long long)(i + GH) * g.pitchW + WPAD + (col >> 5)] >> (col & 31)) & 1u);
     if (R) {
-      const RT rv = Rp[(long long)(i + GH) * g.pitchB + col];
+      const RT rv = Rp[(long long)(i + GH) * g.pitchB + CPAD + col];
       R[e] = (sizeof(RT) == 1) ? (double)rv * rq : (double)rv;
     }
     if (Q) {

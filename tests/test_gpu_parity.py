@@ -109,6 +109,11 @@ F32_CASES = [
     ("halfR_L96", dict(C1, L=96, rep_gain_C=0.5)),          # int8 in units of 1/2
     ("fracR_L72", dict(C1, L=72, rep_gain_C=0.3, delta_R_D=0.7, use_second_order=True)),  # fp32 R
     ("act_m1_L520", dict(C2, L=520, use_second_order=False, r=3.0)),
+    # 128-aligned sides take the TMA/SWAR fast path (spgg_fast.cuh)
+    ("fast_act_m1_L384", dict(C2, L=384, use_second_order=False, r=3.0, reward_weight_payoff=0.9)),
+    ("fast_act_m2_L256", dict(C2, L=256)),
+    ("fast_rep_m2_L640", dict(C1, L=640, use_second_order=True)),
+    ("fast_halfR_L128", dict(C1, L=128, rep_gain_C=0.5, R_min=-7, R_max=7.5)),
 ]
 
 
@@ -137,6 +142,37 @@ def test_fp32_philox_vs_oracle_bit_exact(name, p):
     np.testing.assert_allclose(rows[:, 4:11], rows_o[:, 4:11], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(rows[:, 18:31], rows_o[:, 18:31], rtol=1e-4, atol=1e-3)
     eng.close()
+
+
+@pytest.mark.parametrize("second", [False, True])
+@pytest.mark.parametrize("state", ["reputation", "action"])
+def test_fast_path_equals_general_path(monkeypatch, second, state):
+    """The TMA/SWAR kernel and the general kernel are two layouts of the same arithmetic."""
+    L, n = 256, 25
+    p = full_params(dict(C1, L=L, use_second_order=second, state_representation=state))
+    rs = np.random.RandomState(21)
+    Q0 = rs.uniform(-0.01, 0.01, (L, L, 2, 2))
+    S0 = rs.randint(0, 2, (L, L))
+    outs = []
+    for no_fast in (False, True):
+        if no_fast:
+            monkeypatch.setenv("SPGG_NO_FAST", "1")
+        else:
+            monkeypatch.delenv("SPGG_NO_FAST", raising=False)
+        eng = _engine(p, seeds=31, precision="fp32")
+        eng.set_state(S0, np.zeros((L, L)), Q0)
+        eng.step(n)
+        outs.append(eng.get_state() + (eng.stats(),))
+        eng.close()
+    for a, b in zip(*outs):
+        if a.ndim == 2 and a.shape[1] == 40:
+            exact = [c for c in range(18) if c != 10] + [31, 32, 33]
+            assert np.array_equal(a[:, exact], b[:, exact])
+            # fp32 partial sums are grouped differently by the two layouts
+            np.testing.assert_allclose(a[:, 10], b[:, 10], rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(a[:, 18:31], b[:, 18:31], rtol=1e-5, atol=1e-4)
+        else:
+            assert np.array_equal(a, b)
 
 
 def test_fp32_replay_draws_vs_oracle():
