@@ -177,9 +177,14 @@ static size_t step_smem(int mode, int TR) {
 
 // ---------------------------------------------------------------- fast path plumbing
 typedef void (*fast_fn_t)(const FastMaps, KArgs);
-static fast_fn_t pick_fast(int M, int action) {
-  if (M == 2) return action ? k_step_fast<2, true> : k_step_fast<2, false>;
-  return action ? k_step_fast<1, true> : k_step_fast<1, false>;
+template <int M, bool ACTION>
+static fast_fn_t pick_fast2(int upd, int sel) {
+  if (upd) return sel ? k_step_fast<M, ACTION, true, true> : k_step_fast<M, ACTION, true, false>;
+  return k_step_fast<M, ACTION, false, true>;
+}
+static fast_fn_t pick_fast(int M, int action, int upd, int sel) {
+  if (M == 2) return action ? pick_fast2<2, true>(upd, sel) : pick_fast2<2, false>(upd, sel);
+  return action ? pick_fast2<1, true>(upd, sel) : pick_fast2<1, false>(upd, sel);
 }
 static size_t fast_smem(int M) { return M == 2 ? FastSmem<2>::kTotal : FastSmem<1>::kTotal; }
 typedef void (*gfast_fn_t)(const CUtensorMap, GArgs);
@@ -310,8 +315,11 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, h->threads, h->smem_step));
   }
   if (h->fast) {
-    fast_fn_t ff = pick_fast(h->M, h->action);
-    CUDA_TRY(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem(h->M)));
+    for (int v = 0; v < 3; ++v) {
+      fast_fn_t fv = pick_fast(h->M, h->action, v != 2, v != 1);
+      CUDA_TRY(cudaFuncSetAttribute(fv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem(h->M)));
+    }
+    fast_fn_t ff = pick_fast(h->M, h->action, 1, 1);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff, FTHREADS, fast_smem(h->M)));
     CUDA_TRY(cudaFuncSetAttribute(pick_gfast(h->M), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfast_smem(h->M)));
   }
@@ -611,7 +619,8 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
   if (h->fast && !replay) {
-    fast_fn_t ff = pick_fast(h->M, h->action);
+    if (!do_update && !do_select) return SPGG_OK;
+    fast_fn_t ff = pick_fast(h->M, h->action, do_update, do_select);
     ff<<<h->g.ctas_per_rep * h->n_rep, FTHREADS, fast_smem(h->M), st>>>(h->fmaps[h->cur], a);
   } else {
     step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);

@@ -49,9 +49,12 @@ struct FastSmem {
   static constexpr int kOffSt = kOffSN + FTR * FROWB;            // post-action state flags
   static constexpr int kOffVal = kOffSt + FTR * FROWB;           // reward floats, rows -M..FTR+M-1
   static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
-  static constexpr int kOffRed = kOffTab + 256 * 4;
-  static constexpr int kOffBar = kOffRed + 8 * NSTAT * 8;
-  static constexpr int kTotal = kOffBar + 64;
+  static constexpr int kOffBar = kOffTab + 256 * 4;            // 2 tile barriers + 16 per-warp Q barriers
+  static constexpr int kOffFlag = kOffBar + 18 * 8;            // "last CTA" flag
+  static constexpr int kOffRc = kOffFlag + 16;                 // RepConst copy
+  static constexpr int kOffQ = (kOffRc + (int)sizeof(RepConst) + 127) / 128 * 128;  // per warp: 2 x 128 float4
+  static constexpr int kOffRed = kOffQ;                        // the final reduction reuses the Q buffers
+  static constexpr int kTotal = kOffQ + (FTHREADS / 32) * 2 * TC * 16;
 };
 
 // ---- PTX helpers: mbarrier + TMA (Blackwell guide: TMA tile load with mbarrier signalling)
@@ -89,6 +92,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
+// contiguous global -> shared bulk copy (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
@@ -109,17 +119,18 @@ struct FastMaps {
   CUtensorMap st_code, st_R, st_S;  // tile stores into the planes of iteration j+1
 };
 
-template <int M, bool ACTION>
-__global__ void __launch_bounds__(FTHREADS, 3)
-k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
+#ifndef SPGG_FAST_MINBLOCKS
+#define SPGG_FAST_MINBLOCKS 3
+#endif
+// UPD / SEL are compile-time so the four sites a thread handles per row form one straight-line
+// block the scheduler can interleave.
+template <int M, bool ACTION, bool UPD, bool SEL>
+__device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &a) {
   typedef FastSmem<M> SM;
   constexpr int NK = (M == 2) ? 12 : 4;
+  constexpr bool upd = UPD, sel = SEL;
   const Geom &g = a.g;
   const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
-  const int stop = a.stop_at[rep];
-  if (stop >= 0 && a.j > stop) return;
-  const bool upd = a.do_update != 0;
-  const bool sel = (a.do_select != 0) && !(stop >= 0 && a.j == stop);
 
   extern __shared__ __align__(128) unsigned char smem_fast[];
   unsigned char *smem = smem_fast;
@@ -135,8 +146,8 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   uint8_t *out_code = smem + SM::kOutCode;
   int8_t *out_R = reinterpret_cast<int8_t *>(smem + SM::kOutR);
   uint32_t *out_S = reinterpret_cast<uint32_t *>(smem + SM::kOutS);
-  __shared__ RepConst s_rc;
-  __shared__ int s_is_last;
+  RepConst &s_rc = *reinterpret_cast<RepConst *>(smem + SM::kOffRc);
+  int &s_is_last = *reinterpret_cast<int *>(smem + SM::kOffFlag);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < (int)(sizeof(RepConst) / 4); i += FTHREADS)
@@ -166,38 +177,59 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   const bool has_ratio = rc.has_ratio != 0;
   const uint32_t seed_lo = rc.seed_lo, seed_hi = rc.seed_hi;
 
-  // per-thread statistics: exact packed 16-bit counters + fp32 partial sums.
-  // class = C_old*2 + coop (spgg.py:383,419-420); pk_n01 holds classes 0 (low) and 1 (high), pk_n23 2 and 3
-  uint32_t pk_n01 = 0, pk_n23 = 0;
-  uint32_t pk_sn01 = 0, pk_sn23 = 0;              // sums of SigmaN per class (flushed every 32 tiles)
-  uint32_t pk_g01 = 0, pk_g23 = 0, pk_g45 = 0;    // group histogram, two 16-bit bins per word
-  uint32_t pk_best = 0;                           // low: #best>0, high: ... with a second-order arg-max
+  // per-thread statistics: exact 32-bit integer counters + fp32 partial sums.
+  // class = C_old*2 + coop (spgg.py:383,419-420)
+  uint32_t cls_n[4] = {0, 0, 0, 0}, cls_sn[4] = {0, 0, 0, 0};  // counts and sums of SigmaN per class
+  uint32_t grp[6] = {0, 0, 0, 0, 0, 0};                         // #groups with k defectors
+  uint32_t pk_best = 0;   // low 16: #best>0, high 16: ... with a second-order arg-max
   uint32_t n_sel = 0;
   int sum_r = 0;
-  unsigned long long tot_sn[4] = {0, 0, 0, 0};
   float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
   float s_ni = 0.f, s_ratio = 0.f;
 
   const int n_tiles = g.n_tx * g.n_ty;
-  auto issue = [&](int tile, int st) {
-    const int r0 = (tile / g.n_tx) * FTR, c0 = (tile % g.n_tx) * TC;
+  // tile walk without divisions: (ty, tx) advance by (d_ty, d_tx) with a carry
+  const int d_ty = g.ctas_per_rep / g.n_tx, d_tx = g.ctas_per_rep - d_ty * g.n_tx;
+  auto issue = [&](int ty_, int tx_, int st) {
+    const int r0 = ty_ * FTR, c0 = tx_ * TC;
     unsigned char *base = smem + st * SM::kStageBytes;
     mbar_expect_tx(&bars[st], SM::kTxBytes);
     tma_load_3d(base + SM::kStageCode, &tm.ld_code, &bars[st], c0, r0 + GH - M, rep);
     tma_load_3d(base + SM::kStageR, &tm.ld_R, &bars[st], c0, r0 + GH - M, rep);
     tma_load_3d(base + SM::kStageS, &tm.ld_S, &bars[st], c0 >> 3, r0 + GH - 2, rep);
   };
-  if (tid == 0 && cta < n_tiles) issue(cta, 0);
+  int ty = cta / g.n_tx, tx = cta - ty * g.n_tx;
+  if (tid == 0 && cta < n_tiles) issue(ty, tx, 0);
+
+  // per-warp Q pipeline: the 2 KB row segment (128 float4) a warp handles next is fetched by
+  // one bulk copy into the warp's own double buffer while the warp works on the current one
+  uint64_t *qbar = bars + 2 + warp * 2;
+  float4 *sQ = reinterpret_cast<float4 *>(smem + SM::kOffQ) + warp * (2 * TC);
+  if (lane == 0) {
+    mbar_init(&qbar[0], 1);
+    mbar_init(&qbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto q_issue = [&](const float4 *src, int buf) {
+    mbar_expect_tx(&qbar[buf], TC * 16);
+    bulk_load_1d(sQ + buf * TC, src, TC * 16, &qbar[buf]);
+  };
+  uint32_t q_it = 0;  // row segments this warp has consumed
+  if (lane == 0 && cta < n_tiles) q_issue(Qp + ((long long)(ty * FTR + warp) * g.L + tx * TC), 0);
 
   int tiles_done = 0, stage = 0;
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
-    const int ty = tile / g.n_tx, tx = tile - ty * g.n_tx;
     const int r0 = ty * FTR, c0 = tx * TC;
+    // coordinates of this CTA's next tile
+    int nty = ty + d_ty, ntx = tx + d_tx;
+    if (ntx >= g.n_tx) { ntx -= g.n_tx; ++nty; }
+    const bool has_next = tile + g.ctas_per_rep < n_tiles;
     // prefetch the next tile into the other stage (its readers passed the barrier that
     // closes the previous iteration)
     if (tid == 0) {
-      if (tile + g.ctas_per_rep < n_tiles) issue(tile + g.ctas_per_rep, stage ^ 1);
-      if (sel) tma_store_wait_read();  // the previous tile's stores have left out_* 
+      if (has_next) issue(nty, ntx, stage ^ 1);
+      if (sel) tma_store_wait_read();  // the previous tile's stores have left out_*
     }
     mbar_wait(&bars[stage], (uint32_t)(tiles_done >> 1) & 1u);  // a stage completes once every 2 tiles
     const unsigned char *st_base = smem + stage * SM::kStageBytes;
@@ -271,6 +303,39 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
         wSt[row * FROWW + w] = flags;
       }
     }
+    // ---- phase A4: integer statistics of iteration j straight from the staged words
+    if (upd) {
+      for (int e = tid; e < FTR * 32; e += FTHREADS) {
+        const int row = e >> 5, w = (e & 31) + 4;
+        const uint32_t cw = st_code[(row + M) * FROWW + w];
+        const uint32_t Cb = (cw >> 2) & 0x01010101u, Ab = (cw >> 1) & 0x01010101u;  // was-cooperator, cooperates
+        const uint32_t m3 = Cb & Ab, m2 = Cb ^ m3, m1 = Ab ^ m3, m0 = 0x01010101u ^ (Cb | Ab);
+        const uint32_t sn = (cw >> 3) & 0x1F1F1F1Fu;
+        cls_n[0] = __dp4a(m0, 0x01010101u, cls_n[0]); cls_sn[0] = __dp4a(sn, m0, cls_sn[0]);
+        cls_n[1] = __dp4a(m1, 0x01010101u, cls_n[1]); cls_sn[1] = __dp4a(sn, m1, cls_sn[1]);
+        cls_n[2] = __dp4a(m2, 0x01010101u, cls_n[2]); cls_sn[2] = __dp4a(sn, m2, cls_sn[2]);
+        cls_n[3] = __dp4a(m3, 0x01010101u, cls_n[3]); cls_sn[3] = __dp4a(sn, m3, cls_sn[3]);
+      }
+      // defectors per 5-site group (spgg.py:586-592), bit-sliced: one thread = 32 sites
+      if (tid < FTR * 4) {
+        const int row = (tid >> 2) + 2, bw = (tid & 3) + 4;
+        const uint32_t *bp = st_S + row * (FSROWB / 4) + bw;
+        const uint32_t c = bp[0], u = bp[-(FSROWB / 4)], d = bp[FSROWB / 4];
+        const uint32_t l = (c << 1) | (bp[-1] >> 31), r = (c >> 1) | (bp[1] << 31);
+        const uint32_t s1 = c ^ u ^ d, c1 = (c & u) | (d & (c | u));
+        const uint32_t b0 = s1 ^ l ^ r, c2 = (s1 & l) | (r & (s1 | l));
+        const uint32_t b1 = c1 ^ c2, b2 = c1 & c2;
+        grp[0] += __popc(~b0 & ~b1 & ~b2); grp[1] += __popc(b0 & ~b1 & ~b2);
+        grp[2] += __popc(~b0 & b1 & ~b2);  grp[3] += __popc(b0 & b1 & ~b2);
+        grp[4] += __popc(~b0 & ~b1 & b2);  grp[5] += __popc(b0 & ~b1 & b2);
+      }
+    }
+    {
+      for (int e = tid; e < FTR * 32; e += FTHREADS) {
+        const int row = e >> 5, w = (e & 31) + 4;
+        sum_r = __dp4a((int)st_R[(row + M) * FROWW + w], 0x01010101, sum_r);  // spgg.py:394
+      }
+    }
     __syncthreads();
     // ---- phase B: N = cooperators in the 5-site group centred on each site (spgg.py:23-36),
     // flat over rows -1..FTR (words 0-2 / 37-39 of a row hold don't-care values)
@@ -290,7 +355,6 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
 
     // ---- main phase: warp = one 128-site row segment, lane = 4 sites strided by 32
     const uint8_t *bC = reinterpret_cast<const uint8_t *>(wC);
-    const uint8_t *bN = reinterpret_cast<const uint8_t *>(wN);
     const uint8_t *bSN = reinterpret_cast<const uint8_t *>(wSN);
     const uint8_t *bSt = reinterpret_cast<const uint8_t *>(wSt);
     const uint8_t *bCode = reinterpret_cast<const uint8_t *>(st_code);
@@ -299,23 +363,32 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
 #pragma unroll 1
     for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
       float4 *qrow = qtile + (long long)rr * g.L;
-      float4 qn = __ldcs(qrow);
+      // fetch the row segment after this one (same tile, or the first one of this warp's next tile)
+      {
+        const bool same_tile = rr + FTHREADS / 32 < FTR;
+        const float4 *nsrc = same_tile ? (qrow - lane) + (long long)(FTHREADS / 32) * g.L
+                                       : Qp + ((long long)(nty * FTR + warp) * g.L + ntx * TC);
+        __syncwarp();  // every lane is done reading the buffer about to be refilled
+        if (lane == 0 && (same_tile || has_next)) q_issue(nsrc, (q_it + 1) & 1);
+      }
+      const float4 *qbuf = sQ + (q_it & 1) * TC + lane;
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel) {
         // counter = (column group, global row, iteration, 0); one call -> 4 sites
         philox4x32_10((uint32_t)(((c0 >> 7) << 5) | lane), (uint32_t)(g.row0 + r0 + rr),
                       (uint32_t)(a.j + 1), 0u, seed_lo, seed_hi, w4);
       }
+      mbar_wait(&qbar[q_it & 1], (q_it >> 1) & 1u);
+      ++q_it;
       const int rb = rr * FROWB + CPAD + lane;  // byte offset of (rr, lane) in a tile-row-indexed plane
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
         const int bo = rb + 32 * k4;
-        float q0_ = qn.x, q1_ = qn.y, q2_ = qn.z, q3_ = qn.w;
-        if (k4 < 3) qn = __ldcs(qrow + 32 * (k4 + 1));
+        const float4 qv = qbuf[32 * k4];
+        float q0_ = qv.x, q1_ = qv.y, q2_ = qv.z, q3_ = qv.w;
         const int r_old = bR[bo + M * FROWB];
         const int Ccur = bC[bo + 2 * FROWB];
         const int s_new = ACTION ? Ccur : (int)bSt[bo];
-        sum_r += r_old;
         if (upd) {
           const int crow = bo + M * FROWB;
           const uint32_t code = bCode[crow];
@@ -351,14 +424,8 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
           q1_ = (ee == 1) ? qfin : q1_;
           q2_ = (ee == 2) ? qfin : q2_;
           q3_ = (ee == 3) ? qfin : q3_;
-          const uint32_t inc = 1u << (coop << 4);
-          const uint32_t snv = (code >> 3) << (coop << 4);
-          if (wasC) { pk_n23 += inc; pk_sn23 += snv; } else { pk_n01 += inc; pk_sn01 += snv; }
-          if (has_ratio && coop) s_ratio += sm_ratio[code >> 1];
+          if (has_ratio) s_ratio += sm_ratio[code >> 1];  // zero for defecting codes
           if (best > 0.f) pk_best += second ? 0x10001u : 1u;
-          const int nd = 5 - (int)bN[bo + FROWB];                               // spgg.py:586-592
-          const uint32_t gone = 1u << ((nd & 1) << 4);
-          if (nd < 2) pk_g01 += gone; else if (nd < 4) pk_g23 += gone; else pk_g45 += gone;
           const float m = wasC ? 1.0f : 0.0f;
           sq0 += q0_; sq1 += q1_; sq2 += q2_; sq3 += q3_;
           sc0 = fmaf(m, q0_, sc0); sc1 = fmaf(m, q1_, sc1); sc2 = fmaf(m, q2_, sc2); sc3 = fmaf(m, q3_, sc3);
@@ -370,7 +437,6 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
           const float ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
           const int greedy = (gb > ga) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
           const int a_new = explore ? rnd : greedy;  // algorithms.py:109
-          n_sel += (a_new ^ 1);
           int t = r_old + (a_new == 0 ? gain_i : -loss_i);  // spgg.py:321-323
           t = min(max(t, rmin_i), rmax_i);
           const uint32_t cnew = ((uint32_t)bSN[bo] << 3) | (Ccur << 2) | ((a_new ^ 1) << 1) | s_new;
@@ -382,15 +448,10 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
         }
       }
     }
-    // 16-bit fields: SigmaN <= 25 per site, <= 8 sites per tile and thread
-    if ((tiles_done & 31) == 31) {
-      tot_sn[0] += pk_sn01 & 0xffffu; tot_sn[1] += pk_sn01 >> 16;
-      tot_sn[2] += pk_sn23 & 0xffffu; tot_sn[3] += pk_sn23 >> 16;
-      pk_sn01 = pk_sn23 = 0;
-    }
     if (sel) fence_proxy_async();  // make out_* visible to the TMA engine
     __syncthreads();               // everyone is done with this stage, the work planes and out_*
     if (sel) {
+      if (tid < FTR * 4) n_sel += 32 - __popc(out_S[tid]);  // cooperating actions just chosen
       if (tid == 0) {
         tma_store_3d(&tm.st_code, out_code, CPAD + c0, r0 + GH, rep);
         tma_store_3d(&tm.st_R, out_R, CPAD + c0, r0 + GH, rep);
@@ -420,25 +481,22 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
         __syncthreads();  // out_* is read above; the next tile overwrites it
       }
     }
+    ty = nty; tx = ntx;
   }
-  tot_sn[0] += pk_sn01 & 0xffffu; tot_sn[1] += pk_sn01 >> 16;
-  tot_sn[2] += pk_sn23 & 0xffffu; tot_sn[3] += pk_sn23 >> 16;
   if (tid == 0 && sel) tma_store_wait_all();
 
   // ---- per-CTA partial row, then the last CTA of the replica folds them in a fixed order
   double v[NSTAT];
 #pragma unroll
   for (int z = 0; z < NSTAT; ++z) v[z] = 0.0;
-  const double n0 = (double)(pk_n01 & 0xffffu), n1 = (double)(pk_n01 >> 16);
-  const double n2 = (double)(pk_n23 & 0xffffu), n3 = (double)(pk_n23 >> 16);
+  const double n0 = (double)cls_n[0], n1 = (double)cls_n[1], n2 = (double)cls_n[2], n3 = (double)cls_n[3];
   v[ST_NC_OLD] = n2 + n3; v[ST_N_CD] = n2; v[ST_N_DC] = n1; v[ST_NC_NEW] = n1 + n3;
   v[ST_SUM_P] = n0; v[ST_SUM_P_C] = n1; v[ST_SUM_P_D] = n2; v[ST_SUM_WP_P] = n3;  // raw class counts until the fold
 #pragma unroll
-  for (int z = 0; z < 4; ++z) v[ST_X_SN0 + z] = (double)tot_sn[z];
+  for (int z = 0; z < 4; ++z) v[ST_X_SN0 + z] = (double)cls_sn[z];
   v[ST_SUM_RATIO] = (double)s_ratio;
-  v[ST_GROUP0 + 0] = (double)(pk_g01 & 0xffffu); v[ST_GROUP0 + 1] = (double)(pk_g01 >> 16);
-  v[ST_GROUP0 + 2] = (double)(pk_g23 & 0xffffu); v[ST_GROUP0 + 3] = (double)(pk_g23 >> 16);
-  v[ST_GROUP0 + 4] = (double)(pk_g45 & 0xffffu); v[ST_GROUP0 + 5] = (double)(pk_g45 >> 16);
+#pragma unroll
+  for (int z = 0; z < 6; ++z) v[ST_GROUP0 + z] = (double)grp[z];
   v[ST_SUM_R] = (double)sum_r;
   v[ST_SUM_Q + 0] = (double)sq0; v[ST_SUM_Q + 1] = (double)sq1; v[ST_SUM_Q + 2] = (double)sq2; v[ST_SUM_Q + 3] = (double)sq3;
   v[ST_SUM_Q_C + 0] = (double)sc0; v[ST_SUM_Q_C + 1] = (double)sc1; v[ST_SUM_Q_C + 2] = (double)sc2; v[ST_SUM_Q_C + 3] = (double)sc3;
@@ -495,6 +553,19 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
       if (nsel == 0.0 || nsel == (double)g.site_stride) a.stop_at[rep] = a.j + 1;
     }
   }
+}
+
+template <int M, bool ACTION, bool UPD, bool SEL>
+__global__ void __launch_bounds__(FTHREADS, SPGG_FAST_MINBLOCKS)
+k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
+  const int rep = blockIdx.x / a.g.ctas_per_rep;
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  if (SEL && stop >= 0 && a.j == stop) {  // uniform lattice: finish iteration j, choose nothing (spgg.py:405)
+    if constexpr (UPD) step_fast_body<M, ACTION, true, false>(tm, a);
+    return;
+  }
+  step_fast_body<M, ACTION, UPD, SEL>(tm, a);
 }
 
 // lattice-global max |reward difference| of iteration j (spgg.py:486-488), fast path: the code
