@@ -517,13 +517,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  if (tid < NSTAT) {
-    double x = 0.0;
-    const double *pp = a.partials + (long long)rep * g.ctas_per_rep * NSTAT + tid;
-    for (int c = 0; c < g.ctas_per_rep; ++c) x += __ldcg(pp + (long long)c * NSTAT);
-    sm_red[tid] = x;
-  }
-  __syncthreads();
+  fold_partials(a.partials + (long long)rep * g.ctas_per_rep * NSTAT, g.ctas_per_rep, sm_red);
   if (tid == 0) {
     double *row = a.stats + ((long long)rep * a.cap + a.rel) * NSTAT;
     double *s = sm_red;

@@ -273,6 +273,27 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *sm_red /* 
   __syncthreads();
 }
 
+// Last CTA of a replica: fold the per-CTA partial rows in a fixed order (deterministic) using
+// the whole block: group q of NSTAT threads adds CTAs q, q+G, q+2G, ...; the G group sums
+// are then added in order.  Result in sm_red[0..NSTAT).
+__device__ __forceinline__ void fold_partials(const double *pp, int n_ctas, double *sm_red /* [8][NSTAT] */) {
+  const int groups = min((int)blockDim.x / NSTAT, 8);
+  const int q = threadIdx.x / NSTAT, z = threadIdx.x - q * NSTAT;
+  if (q < groups) {
+    double x = 0.0;
+#pragma unroll 4
+    for (int c = q; c < n_ctas; c += groups) x += __ldcg(pp + (long long)c * NSTAT + z);
+    sm_red[q * NSTAT + z] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NSTAT) {
+    double x = sm_red[threadIdx.x];
+    for (int k = 1; k < groups; ++k) x += sm_red[k * NSTAT + threadIdx.x];
+    sm_red[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 
@@ -774,13 +795,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  if (threadIdx.x < NSTAT) {
-    double x = 0.0;
-    const double *pp = a.partials + (long long)rep * g.ctas_per_rep * NSTAT + threadIdx.x;
-    for (int c = 0; c < g.ctas_per_rep; ++c) x += __ldcg(pp + (long long)c * NSTAT);
-    sm_red[threadIdx.x] = x;
-  }
-  __syncthreads();
+  fold_partials(a.partials + (long long)rep * g.ctas_per_rep * NSTAT, g.ctas_per_rep, sm_red);
   if (threadIdx.x == 0) {
     double *row = a.stats + ((long long)rep * a.cap + a.rel) * NSTAT;
     double *s = sm_red;

@@ -42,3 +42,33 @@ def legacy_stream(seed, L, n):
         u[t] = rs.rand(L, L)
         b[t] = rs.randint(0, 2, (L, L))
     return Q0, S0, u, b
+
+
+def launch_ranks(argv, world, timeout=600, extra_env=None):
+    """Start ``world`` copies of tests/strip_worker.py (one rank each, rendezvous on
+    127.0.0.1) and return their (returncode, output) pairs."""
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "strip_worker.py")
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env.update(extra_env or {})
+        procs.append(subprocess.Popen([sys.executable, worker] + [str(a) for a in argv], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    out = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            o, _ = p.communicate()
+            o += "\n[timeout]"
+        out.append((p.returncode, o))
+    return out

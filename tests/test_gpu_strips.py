@@ -1,0 +1,40 @@
+"""Row strips with the real kernels: an N-strip run equals the single-handle run bit for
+bit (S, R, Q, integer statistics; float sums to tolerance - the summation order differs).
+On a one-GPU box the ranks share cuda:0 and exchange through gloo (host-staged halos);
+with >= 2 GPUs the NCCL path (device buffers, NVLink) is tested as well."""
+import pytest
+
+from helpers import launch_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("precision,second,state,L,world", [
+    ("fp32", 0, "reputation", 256, 2),      # fast path (TMA) strips
+    ("fp32", 1, "action", 256, 4),
+    ("fp32", 1, "reputation", 100, 3),      # general path, ragged strips
+    ("fp64", 0, "reputation", 64, 2),
+])
+def test_strips_equal_single_lattice_gloo(precision, second, state, L, world):
+    res = launch_ranks(["gpu", "gloo", precision, second, state, L, 12], world, timeout=600)
+    for rc, out in res:
+        assert rc == 0, out
+
+
+@pytest.mark.parametrize("precision,second,state,L", [
+    ("fp32", 0, "reputation", 512),
+    ("fp32", 1, "reputation", 384),
+])
+def test_strips_equal_single_lattice_nccl(precision, second, state, L):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = min(n, 4)
+    res = launch_ranks(["gpu", "nccl", precision, second, state, L, 12], world, timeout=600)
+    for rc, out in res:
+        assert rc == 0, out
