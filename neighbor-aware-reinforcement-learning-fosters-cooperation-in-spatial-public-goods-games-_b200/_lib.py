@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspgg_b200.so")
+# SPGG_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SPGG_B200_LIB") or os.path.join(_HERE, "libspgg_b200.so")
 NSTAT = 40
 
 # stat-row columns (include/spgg.h: enum spgg_stat)

@@ -212,6 +212,29 @@ static int make_map(CUtensorMap *map, void *base, uint64_t row_bytes, uint64_t n
   return SPGG_OK;
 }
 
+// Q table of the fast path: bytes (128 = 8 sites, L/8 chunks, rows, replicas), boxes of one
+// 128-site row segment, 128-byte swizzle so that a lane's four consecutive float4 are
+// conflict-free in shared memory
+static int make_map_q(CUtensorMap *map, void *base, uint64_t L, uint64_t n_rows, uint64_t n_rep) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SPGG_E_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  const cuuint64_t dims[4] = {128, L / 8, n_rows, n_rep};
+  const cuuint64_t strides[3] = {128, L * 16, n_rows * L * 16};
+  const cuuint32_t box[4] = {128, TC / 8, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SPGG_E_CUDA, "cuTensorMapEncodeTiled (Q) failed (%d)", (int)r);
+  return SPGG_OK;
+}
+
 // ---------------------------------------------------------------- lifetime
 extern "C" int spgg_abi_version(void) { return SPGG_ABI_VERSION; }
 extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
@@ -363,6 +386,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
       if (!e) e = make_map(&fm.st_code, h->d_code[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
       if (!e) e = make_map(&fm.st_R, h->d_R[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
       if (!e) e = make_map(&fm.st_S, h->d_S[i ^ 1], (uint64_t)g.pitchW * 4, nrows, n_replicas, (uint64_t)g.bits_stride * 4, TC / 8, FTR);
+      if (!e) e = make_map_q(&fm.q, h->d_Q, (uint64_t)g.L, (uint64_t)g.rows, (uint64_t)n_replicas);
       if (e) { free_all(h); delete h; return e; }
     }
   }
@@ -618,6 +642,22 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   a.b = replay ? h->d_b + (size_t)draw * h->g.site_stride : nullptr;
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
+#ifdef SPGG_TRACE
+  {  // debug builds only: dump the per-CTA timeline of the previous fused launch
+    static unsigned long long *d_trace = nullptr;
+    static int n_dump = 0;
+    const int n_cta = h->g.ctas_per_rep * h->n_rep;
+    if (!d_trace) { cudaMalloc(&d_trace, sizeof(unsigned long long) * 4 * 65536); cudaMemset(d_trace, 0, sizeof(unsigned long long) * 4 * 65536); }
+    else if (getenv("SPGG_TRACE_FILE") && n_dump < 3 && do_update && do_select) {
+      std::vector<unsigned long long> t(4 * (size_t)n_cta);
+      cudaDeviceSynchronize();
+      cudaMemcpy(t.data(), d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+      char name[256]; snprintf(name, sizeof(name), "%s.%d", getenv("SPGG_TRACE_FILE"), n_dump++);
+      FILE *f = fopen(name, "wb"); if (f) { fwrite(t.data(), 8, t.size(), f); fclose(f); }
+    }
+    a.trace = d_trace;
+  }
+#endif
   if (h->fast && !replay) {
     if (!do_update && !do_select) return SPGG_OK;
     fast_fn_t ff = pick_fast(h->M, h->action, do_update, do_select);

@@ -22,11 +22,17 @@
 
 namespace spgg {
 
-constexpr int FTR = 16;            // tile rows
+#ifndef SPGG_FTR
+#define SPGG_FTR 16
+#endif
+#ifndef SPGG_FTHREADS
+#define SPGG_FTHREADS 256
+#endif
+constexpr int FTR = SPGG_FTR;      // tile rows
 constexpr int FROWB = 160;         // staged row bytes of code / R: 16 ghost + 128 + 16 ghost
 constexpr int FROWW = FROWB / 4;   // the same in 32-bit words
 constexpr int FSROWB = 48;         // staged row bytes of strategy bits: 16 + 16 + 16
-constexpr int FTHREADS = 256;
+constexpr int FTHREADS = SPGG_FTHREADS;
 
 template <int M>
 struct FastSmem {
@@ -44,17 +50,19 @@ struct FastSmem {
   // work planes, all with the staged row geometry (row r, word w <-> tile cols 4(w-4)..4(w-4)+3),
   // one guard row before the first so flat stencils may read one word before a plane
   static constexpr int kOffC = kOutS + 256 + FROWB;              // cooperator flags, rows -2..FTR+1
-  static constexpr int kOffN = kOffC + (FTR + 4) * FROWB;        // N, rows -1..FTR
-  static constexpr int kOffSN = kOffN + (FTR + 2) * FROWB;       // SigmaN, rows 0..FTR-1
-  static constexpr int kOffSt = kOffSN + FTR * FROWB;            // post-action state flags
+  static constexpr int kOffSt = kOffC + (FTR + 4) * FROWB + FROWB;  // post-action state flags (one guard row after C)
   static constexpr int kOffVal = kOffSt + FTR * FROWB;           // reward floats, rows -M..FTR+M-1
   static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
-  static constexpr int kOffBar = kOffTab + 256 * 4;            // 2 tile barriers + 16 per-warp Q barriers
-  static constexpr int kOffFlag = kOffBar + 18 * 8;            // "last CTA" flag
+  static constexpr int kOffBar = kOffTab + 256 * 4;            // 2 tile barriers + 3 Q barriers per warp
+  static constexpr int kOffFlag = kOffBar + 32 * 8;            // "last CTA" flag
   static constexpr int kOffRc = kOffFlag + 16;                 // RepConst copy
-  static constexpr int kOffQ = (kOffRc + (int)sizeof(RepConst) + 127) / 128 * 128;  // per warp: 2 x 128 float4
-  static constexpr int kOffRed = kOffQ;                        // the final reduction reuses the Q buffers
-  static constexpr int kTotal = kOffQ + (FTHREADS / 32) * 2 * TC * 16;
+  static constexpr int kOffRed = (kOffRc + (int)sizeof(RepConst) + 127) / 128 * 128;  // final reduction [8][NSTAT]
+  // per warp: kQBufs row segments of 128 float4 (2 KB each), landed by TMA with the 128-byte
+  // swizzle (1024-byte aligned) and written back in place
+  static constexpr int kQBufs = 3;
+  static constexpr int kQBufBytes = TC * 16;
+  static constexpr int kOffQ = (kOffRed + 8 * NSTAT * 8 + 1023) / 1024 * 1024;
+  static constexpr int kTotal = kOffQ + (FTHREADS / 32) * kQBufs * kQBufBytes + 1024;  // + base alignment slack
 };
 
 // ---- PTX helpers: mbarrier + TMA (Blackwell guide: TMA tile load with mbarrier signalling)
@@ -104,6 +112,32 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 4-D tile load / store of the Q table (swizzled), with an L2 eviction-priority hint: Q is
+// streamed once per iteration and must not push the small halo'd planes out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                                 int c1, int c2, int c3, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap *map, const void *src, int c0, int c1,
+                                                  int c2, int c3, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+      ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -117,10 +151,11 @@ __device__ __forceinline__ uint32_t sh_2(uint32_t a, uint32_t b) { return __byte
 struct FastMaps {
   CUtensorMap ld_code, ld_R, ld_S;  // halo'd tile loads from the planes of iteration j
   CUtensorMap st_code, st_R, st_S;  // tile stores into the planes of iteration j+1
+  CUtensorMap q;                    // Q table as (128 B = 8 sites, L/8, rows, replicas), 128-byte swizzle
 };
 
 #ifndef SPGG_FAST_MINBLOCKS
-#define SPGG_FAST_MINBLOCKS 3
+#define SPGG_FAST_MINBLOCKS 2
 #endif
 // UPD / SEL are compile-time so the four sites a thread handles per row form one straight-line
 // block the scheduler can interleave.
@@ -132,11 +167,10 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   const Geom &g = a.g;
   const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
 
-  extern __shared__ __align__(128) unsigned char smem_fast[];
-  unsigned char *smem = smem_fast;
+  extern __shared__ __align__(1024) unsigned char smem_fast[];
+  // the swizzled Q buffers need a 1024-byte aligned base; kTotal carries the slack
+  unsigned char *smem = smem_fast + ((1024u - (smem_u32(smem_fast) & 1023u)) & 1023u);
   uint32_t *wC = reinterpret_cast<uint32_t *>(smem + SM::kOffC);
-  uint32_t *wN = reinterpret_cast<uint32_t *>(smem + SM::kOffN);
-  uint32_t *wSN = reinterpret_cast<uint32_t *>(smem + SM::kOffSN);
   uint32_t *wSt = reinterpret_cast<uint32_t *>(smem + SM::kOffSt);
   float *sm_val = reinterpret_cast<float *>(smem + SM::kOffVal);
   float *sm_tab = reinterpret_cast<float *>(smem + SM::kOffTab);
@@ -150,6 +184,10 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   int &s_is_last = *reinterpret_cast<int *>(smem + SM::kOffFlag);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SPGG_TRACE
+  unsigned long long t_start = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
   for (int i = tid; i < (int)(sizeof(RepConst) / 4); i += FTHREADS)
     reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
   if (tid == 0) {
@@ -198,32 +236,45 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     tma_load_3d(base + SM::kStageR, &tm.ld_R, &bars[st], c0, r0 + GH - M, rep);
     tma_load_3d(base + SM::kStageS, &tm.ld_S, &bars[st], c0 >> 3, r0 + GH - 2, rep);
   };
-  int ty = cta / g.n_tx, tx = cta - ty * g.n_tx;
+  // the column of a tile is skewed by its row ((ty, txs) -> tx = (txs + ty) mod n_tx) so that the
+  // tiles of one CTA sweep all columns: the edge tiles (periodic ghost copies) spread over all CTAs
+  int ty = cta / g.n_tx, txs = cta - ty * g.n_tx;
+  int tx = (txs + ty) % g.n_tx;
   if (tid == 0 && cta < n_tiles) issue(ty, tx, 0);
 
-  // per-warp Q pipeline: the 2 KB row segment (128 float4) a warp handles next is fetched by
-  // one bulk copy into the warp's own double buffer while the warp works on the current one
-  uint64_t *qbar = bars + 2 + warp * 2;
-  float4 *sQ = reinterpret_cast<float4 *>(smem + SM::kOffQ) + warp * (2 * TC);
+  // per-warp Q pipeline: the 2 KB row segment (128 float4) a warp handles next is fetched by one
+  // TMA tile load (128-byte swizzle) into one of the warp's kQBufs buffers while the warp works
+  // on the current one; results are written back in place and leave by a TMA tile store.
+  uint64_t *qbar = bars + 2 + warp * SM::kQBufs;
+  unsigned char *sQ = smem + SM::kOffQ + warp * (SM::kQBufs * SM::kQBufBytes);
+  const uint64_t pol = l2_evict_first_policy();
   if (lane == 0) {
-    mbar_init(&qbar[0], 1);
-    mbar_init(&qbar[1], 1);
+#pragma unroll
+    for (int b = 0; b < SM::kQBufs; ++b) mbar_init(&qbar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto q_issue = [&](const float4 *src, int buf) {
-    mbar_expect_tx(&qbar[buf], TC * 16);
-    bulk_load_1d(sQ + buf * TC, src, TC * 16, &qbar[buf]);
+  auto q_issue = [&](int col8, int row, int buf) {
+    mbar_expect_tx(&qbar[buf], SM::kQBufBytes);
+    tma_load_4d_hint(sQ + buf * SM::kQBufBytes, &tm.q, &qbar[buf], 0, col8, row, rep, pol);
   };
-  uint32_t q_it = 0;  // row segments this warp has consumed
-  if (lane == 0 && cta < n_tiles) q_issue(Qp + ((long long)(ty * FTR + warp) * g.L + tx * TC), 0);
+  // lane l owns the four consecutive sites 4l..4l+3 of a row segment: site s sits in 128-byte
+  // line s>>3 at 16-byte chunk (s&7) ^ (line&7) (CU_TENSOR_MAP_SWIZZLE_128B)
+  int qoff[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    qoff[k] = (lane >> 1) * 128 + ((((lane & 1) * 4 + k) ^ ((lane >> 1) & 7)) << 4);
+  int qb = 0;          // buffer holding the row segment this warp consumes next
+  uint32_t qph = 0;    // bit b: parity the next wait on buffer b expects
+  if (lane == 0 && cta < n_tiles) q_issue((tx * TC) >> 3, ty * FTR + warp, 0);
 
   int tiles_done = 0, stage = 0;
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
     const int r0 = ty * FTR, c0 = tx * TC;
     // coordinates of this CTA's next tile
-    int nty = ty + d_ty, ntx = tx + d_tx;
-    if (ntx >= g.n_tx) { ntx -= g.n_tx; ++nty; }
+    int nty = ty + d_ty, ntxs = txs + d_tx;
+    if (ntxs >= g.n_tx) { ntxs -= g.n_tx; ++nty; }
+    const int ntx = (ntxs + nty) % g.n_tx;
     const bool has_next = tile + g.ctas_per_rep < n_tiles;
     // prefetch the next tile into the other stage (its readers passed the barrier that
     // closes the previous iteration)
@@ -330,96 +381,116 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         grp[4] += __popc(~b0 & ~b1 & b2);  grp[5] += __popc(b0 & ~b1 & b2);
       }
     }
-    {
-      for (int e = tid; e < FTR * 32; e += FTHREADS) {
-        const int row = e >> 5, w = (e & 31) + 4;
-        sum_r = __dp4a((int)st_R[(row + M) * FROWW + w], 0x01010101, sum_r);  // spgg.py:394
-      }
-    }
     __syncthreads();
-    // ---- phase B: N = cooperators in the 5-site group centred on each site (spgg.py:23-36),
-    // flat over rows -1..FTR (words 0-2 / 37-39 of a row hold don't-care values)
-    for (int e = tid; e < (FTR + 2) * FROWW; e += FTHREADS) {
-      const uint32_t *cp = wC + FROWW + e;
-      const uint32_t c = cp[0];
-      wN[e] = c + cp[-FROWW] + cp[FROWW] + sh_l1(cp[-1], c) + sh_r1(c, cp[1]);
-    }
-    __syncthreads();
-    // ---- phase C: SigmaN = sum of N over the 5 groups a site belongs to (spgg.py:373-377)
-    for (int e = tid; e < FTR * FROWW; e += FTHREADS) {
-      const uint32_t *np_ = wN + FROWW + e;
-      const uint32_t c = np_[0];
-      wSN[e] = c + np_[-FROWW] + np_[FROWW] + sh_l1(np_[-1], c) + sh_r1(c, np_[1]);
-    }
-    __syncthreads();
-
-    // ---- main phase: warp = one 128-site row segment, lane = 4 sites strided by 32
-    const uint8_t *bC = reinterpret_cast<const uint8_t *>(wC);
-    const uint8_t *bSN = reinterpret_cast<const uint8_t *>(wSN);
-    const uint8_t *bSt = reinterpret_cast<const uint8_t *>(wSt);
+    // ---- main phase: warp = one 128-site row segment, lane = 4 consecutive sites, so every
+    // byte plane is read one 32-bit word and every reward row one float4 per lane
     const uint8_t *bCode = reinterpret_cast<const uint8_t *>(st_code);
-    const int8_t *bR = reinterpret_cast<const int8_t *>(st_R);
-    float4 *qtile = Qp + ((long long)r0 * g.L + c0 + lane);
 #pragma unroll 1
     for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
-      float4 *qrow = qtile + (long long)rr * g.L;
       // fetch the row segment after this one (same tile, or the first one of this warp's next tile)
       {
         const bool same_tile = rr + FTHREADS / 32 < FTR;
-        const float4 *nsrc = same_tile ? (qrow - lane) + (long long)(FTHREADS / 32) * g.L
-                                       : Qp + ((long long)(nty * FTR + warp) * g.L + ntx * TC);
-        __syncwarp();  // every lane is done reading the buffer about to be refilled
-        if (lane == 0 && (same_tile || has_next)) q_issue(nsrc, (q_it + 1) & 1);
+        const int nrow = same_tile ? r0 + rr + FTHREADS / 32 : nty * FTR + warp;
+        const int ncol8 = (same_tile ? c0 : ntx * TC) >> 3;
+        int nb = qb + 1;
+        if (nb == SM::kQBufs) nb = 0;
+        __syncwarp();  // every lane is done with the segment that last used buffer nb
+        if (lane == 0) {
+          if (upd) tma_store_wait_read_n<1>();  // ... and its tile store has left shared memory
+          if (same_tile || has_next) q_issue(ncol8, nrow, nb);
+        }
       }
-      const float4 *qbuf = sQ + (q_it & 1) * TC + lane;
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel) {
-        // counter = (column group, global row, iteration, 0); one call -> 4 sites
-        philox4x32_10((uint32_t)(((c0 >> 7) << 5) | lane), (uint32_t)(g.row0 + r0 + rr),
+        // counter = (column / 4, global row, iteration, 0); one call -> this lane's 4 sites
+        philox4x32_10((uint32_t)((c0 >> 2) + lane), (uint32_t)(g.row0 + r0 + rr),
                       (uint32_t)(a.j + 1), 0u, seed_lo, seed_hi, w4);
       }
-      mbar_wait(&qbar[q_it & 1], (q_it >> 1) & 1u);
-      ++q_it;
-      const int rb = rr * FROWB + CPAD + lane;  // byte offset of (rr, lane) in a tile-row-indexed plane
+      const int wo = rr * FROWW + (CPAD / 4) + lane;      // word of (rr, 4*lane) in a tile-row-indexed plane
+      const uint32_t RW = st_R[wo + M * FROWW];
+      const uint32_t CW = wC[wo + 2 * FROWW];
+      const uint32_t StW = ACTION ? CW : wSt[wo];          // post-action state flags, 4 sites
+      sum_r = __dp4a((int)RW, 0x01010101, sum_r);          // spgg.py:394
+      uint32_t codeW = 0;
+      float vc[4], vu[4], vd[4], vl[2], vr[2], vu2[4], vd2[4], vul = 0.f, vur = 0.f, vdl = 0.f, vdr = 0.f;
+      const int vb = (rr + M) * FROWB + CPAD + 4 * lane;  // float / byte index of (rr, 4*lane) in the staged planes
+      if (upd) {
+        codeW = st_code[wo + M * FROWW];
+        const float4 c4 = *reinterpret_cast<const float4 *>(sm_val + vb);
+        const float4 u4 = *reinterpret_cast<const float4 *>(sm_val + vb - FROWB);
+        const float4 d4 = *reinterpret_cast<const float4 *>(sm_val + vb + FROWB);
+        vc[0] = c4.x; vc[1] = c4.y; vc[2] = c4.z; vc[3] = c4.w;
+        vu[0] = u4.x; vu[1] = u4.y; vu[2] = u4.z; vu[3] = u4.w;
+        vd[0] = d4.x; vd[1] = d4.y; vd[2] = d4.z; vd[3] = d4.w;
+        if constexpr (M == 2) {
+          const float2 l2 = *reinterpret_cast<const float2 *>(sm_val + vb - 2);
+          const float2 r2 = *reinterpret_cast<const float2 *>(sm_val + vb + 4);
+          vl[0] = l2.x; vl[1] = l2.y; vr[0] = r2.x; vr[1] = r2.y;
+          const float4 uu = *reinterpret_cast<const float4 *>(sm_val + vb - 2 * FROWB);
+          const float4 dd = *reinterpret_cast<const float4 *>(sm_val + vb + 2 * FROWB);
+          vu2[0] = uu.x; vu2[1] = uu.y; vu2[2] = uu.z; vu2[3] = uu.w;
+          vd2[0] = dd.x; vd2[1] = dd.y; vd2[2] = dd.z; vd2[3] = dd.w;
+          vul = sm_val[vb - FROWB - 1]; vur = sm_val[vb - FROWB + 4];
+          vdl = sm_val[vb + FROWB - 1]; vdr = sm_val[vb + FROWB + 4];
+        } else {
+          vl[0] = 0.f; vl[1] = sm_val[vb - 1]; vr[0] = sm_val[vb + 4]; vr[1] = 0.f;
+        }
+      }
+      unsigned char *qbuf = sQ + qb * SM::kQBufBytes;
+      mbar_wait(&qbar[qb], (qph >> qb) & 1u);
+      qph ^= 1u << qb;
+      uint32_t coopW = 0, rnewW = 0;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const int bo = rb + 32 * k4;
-        const float4 qv = qbuf[32 * k4];
+      for (int k = 0; k < 4; ++k) {
+        const float4 qv = *reinterpret_cast<const float4 *>(qbuf + qoff[k]);
         float q0_ = qv.x, q1_ = qv.y, q2_ = qv.z, q3_ = qv.w;
-        const int r_old = bR[bo + M * FROWB];
-        const int Ccur = bC[bo + 2 * FROWB];
-        const int s_new = ACTION ? Ccur : (int)bSt[bo];
+        const int s_new = (StW >> (8 * k)) & 1u;
         if (upd) {
-          const int crow = bo + M * FROWB;
-          const uint32_t code = bCode[crow];
+          const uint32_t code = (codeW >> (8 * k)) & 0xFFu;
           const int s = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
-          const float vx = sm_val[crow];
-          // neighbour-aware term inputs: spgg.py:486-494 (first arg-max wins)
-          float best = 0.f;
-          int bidx = crow;
+          const float vx = vc[k];
+          // neighbour-aware term inputs: spgg.py:486-494, offsets in the order of spgg.py:479-485
+          // ((dx,dy) names the site (i-dx, j-dy)); the first arg-max wins
+          float nv[NK];
+          int no[NK];  // byte offset of the neighbour's code relative to this site's
+          nv[0] = vu[k]; no[0] = -FROWB;                                // (1,0)
+          nv[1] = vd[k]; no[1] = FROWB;                                 // (-1,0)
+          nv[2] = (k == 0) ? vl[1] : vc[(k + 3) & 3]; no[2] = -1;       // (0,1)
+          nv[3] = (k == 3) ? vr[0] : vc[(k + 1) & 3]; no[3] = 1;        // (0,-1)
+          if constexpr (M == 2) {
+            nv[4] = vu2[k]; no[4] = -2 * FROWB;                         // (2,0)
+            nv[5] = vd2[k]; no[5] = 2 * FROWB;                          // (-2,0)
+            nv[6] = (k == 0) ? vl[0] : (k == 1) ? vl[1] : vc[(k + 2) & 3]; no[6] = -2;   // (0,2)
+            nv[7] = (k == 2) ? vr[0] : (k == 3) ? vr[1] : vc[(k + 2) & 3]; no[7] = 2;    // (0,-2)
+            nv[8] = (k == 0) ? vul : vu[(k + 3) & 3]; no[8] = -FROWB - 1;                // (1,1)
+            nv[9] = (k == 3) ? vur : vu[(k + 1) & 3]; no[9] = -FROWB + 1;                // (1,-1)
+            nv[10] = (k == 0) ? vdl : vd[(k + 3) & 3]; no[10] = FROWB - 1;               // (-1,1)
+            nv[11] = (k == 3) ? vdr : vd[(k + 1) & 3]; no[11] = FROWB + 1;               // (-1,-1)
+          }
+          float best = __fsub_rn(nv[0], vx);
+          int boff = no[0];
           bool second = false;
 #pragma unroll
-          for (int k = 0; k < NK; ++k) {
-            const int nidx = crow - c_off[k][0] * FROWB - c_off[k][1];
-            const float d = __fsub_rn(sm_val[nidx], vx);
-            if (k == 0 || d > best) { best = d; bidx = nidx; second = (k >= 4); }
+          for (int q = 1; q < NK; ++q) {
+            const float d = __fsub_rn(nv[q], vx);
+            if (d > best) { best = d; boff = no[q]; second = (q >= 4); }
           }
-          const bool same = (((bCode[bidx] >> 1) & 1u) == (unsigned)coop);
+          const bool same = (((bCode[vb + k + boff] >> 1) & 1u) == (unsigned)coop);
           const int ee = 2 * s + (coop ^ 1);  // index of Q[s][a], a = !coop
           const float qe = sel4<float>(ee, q0_, q1_, q2_, q3_);
-          const float na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
-          const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na, nb), vx), qe);  // algorithms.py:128
-          const float qtd = __fmaf_rn(alpha, td, qe);                           // algorithms.py:131
+          const float na = s_new ? q2_ : q0_, nb_ = s_new ? q3_ : q1_;  // pre-update row of s'
+          const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na, nb_), vx), qe);  // algorithms.py:128
+          const float qtd = __fmaf_rn(alpha, td, qe);                            // algorithms.py:131
           const float lam = __fmul_rn(__fmul_rn(kappa, fmaxf(0.0f, best)), inv_den);  // spgg.py:489
-          const float nu = same ? lam : -lam;                                   // spgg.py:494-495
+          const float nu = same ? lam : -lam;                                    // spgg.py:494-495
           // TD error on the table after the TD write (spgg.py:446-473), for the NI statistic
           const bool hit = (s_new == s);
           const float na2 = (hit && coop) ? qtd : na;
-          const float nb2 = (hit && !coop) ? qtd : nb;
+          const float nb2 = (hit && !coop) ? qtd : nb_;
           const float td2 = __fsub_rn(__fmaf_rn(gamma, fmaxf(na2, nb2), vx), qtd);
-          const float qfin = __fadd_rn(qtd, nu);                                // spgg.py:509
+          const float qfin = __fadd_rn(qtd, nu);                                 // spgg.py:509
           const float an = fabsf(nu);
-          s_ni += __fdividef(an, fabsf(alpha * td2) + an + 1e-8f);              // x100 at the fold; spgg.py:512
+          s_ni += __fdividef(an, fabsf(alpha * td2) + an + 1e-8f);               // x100 at the fold; spgg.py:512
           q0_ = (ee == 0) ? qfin : q0_;
           q1_ = (ee == 1) ? qfin : q1_;
           q2_ = (ee == 2) ? qfin : q2_;
@@ -429,49 +500,95 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           const float m = wasC ? 1.0f : 0.0f;
           sq0 += q0_; sq1 += q1_; sq2 += q2_; sq3 += q3_;
           sc0 = fmaf(m, q0_, sc0); sc1 = fmaf(m, q1_, sc1); sc2 = fmaf(m, q2_, sc2); sc3 = fmaf(m, q3_, sc3);
-          __stcs(qrow + 32 * k4, make_float4(q0_, q1_, q2_, q3_));
+          *reinterpret_cast<float4 *>(qbuf + qoff[k]) = make_float4(q0_, q1_, q2_, q3_);
         }
         if (sel) {
-          const bool explore = (w4[k4] >> 8) < thr;
-          const int rnd = (int)(w4[k4] & 1u);
+          const bool explore = (w4[k] >> 8) < thr;
+          const int rnd = (int)(w4[k] & 1u);
           const float ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
-          const int greedy = (gb > ga) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
+          const int greedy = (gb > ga) ? 1 : 0;      // np.argmax, tie -> 0   algorithms.py:107
           const int a_new = explore ? rnd : greedy;  // algorithms.py:109
+          const int r_old = (int)(int8_t)(RW >> (8 * k));
           int t = r_old + (a_new == 0 ? gain_i : -loss_i);  // spgg.py:321-323
           t = min(max(t, rmin_i), rmax_i);
-          const uint32_t cnew = ((uint32_t)bSN[bo] << 3) | (Ccur << 2) | ((a_new ^ 1) << 1) | s_new;
-          const int oo = rr * TC + lane + 32 * k4;
-          out_code[oo] = (uint8_t)cnew;
-          out_R[oo] = (int8_t)t;
-          const uint32_t word = __ballot_sync(0xffffffffu, a_new);
-          if (lane == 0) out_S[rr * 4 + k4] = word;
+          coopW |= (uint32_t)(a_new ^ 1) << (8 * k);
+          rnewW |= ((uint32_t)t & 0xFFu) << (8 * k);
         }
       }
+      if (sel) {
+        // reward code of iteration j+1: SigmaN<<3 | C_j<<2 | coop<<1 | state, 4 sites per word
+        // SigmaN = cooperators summed over the 5 groups the site belongs to (spgg.py:23-36,
+        // 373-377) = 5 C(x) + 2 (4 nearest + 4 diagonal) + (4 straight second neighbours), bytewise
+        const uint32_t *cp = wC + wo + 2 * FROWW;
+        const uint32_t cl = cp[-1], cr = cp[1];
+        const uint32_t u1 = cp[-FROWW], ul = cp[-FROWW - 1], ur = cp[-FROWW + 1];
+        const uint32_t d1 = cp[FROWW], dl = cp[FROWW - 1], dr = cp[FROWW + 1];
+        const uint32_t ring = u1 + d1 + sh_l1(cl, CW) + sh_r1(CW, cr) + sh_l1(ul, u1) + sh_r1(u1, ur) +
+                              sh_l1(dl, d1) + sh_r1(d1, dr);
+        const uint32_t far4 = cp[-2 * FROWW] + cp[2 * FROWW] + sh_2(cl, CW) + sh_2(CW, cr);
+        const uint32_t SNW = 5u * CW + 2u * ring + far4;
+        const int oo = rr * (TC / 4) + lane;
+        reinterpret_cast<uint32_t *>(out_code)[oo] = (SNW << 3) | (CW << 2) | (coopW << 1) | StW;
+        reinterpret_cast<uint32_t *>(out_R)[oo] = rnewW;
+      }
+      if (upd) {
+        fence_proxy_async();  // the updated segment becomes visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d_hint(&tm.q, qbuf, 0, c0 >> 3, r0 + rr, rep, pol);
+          tma_store_commit();
+        }
+      }
+      if (++qb == SM::kQBufs) qb = 0;
     }
-    if (sel) fence_proxy_async();  // make out_* visible to the TMA engine
-    __syncthreads();               // everyone is done with this stage, the work planes and out_*
+    __syncthreads();  // out_code is complete
     if (sel) {
-      if (tid < FTR * 4) n_sel += 32 - __popc(out_S[tid]);  // cooperating actions just chosen
+      // strategy bits of the tile from the coop flags in out_code: one thread = one 32-site word
+      if (tid < FTR * 4) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(out_code) + tid * 2;
+        const uint4 lo = src[0], hi = src[1];
+        auto nib = [](uint32_t w) { return ((((w >> 1) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; };
+        const uint32_t coopbits = nib(lo.x) | (nib(lo.y) << 4) | (nib(lo.z) << 8) | (nib(lo.w) << 12) |
+                                  (nib(hi.x) << 16) | (nib(hi.y) << 20) | (nib(hi.z) << 24) | (nib(hi.w) << 28);
+        out_S[tid] = ~coopbits;                 // bit = 1: defect
+        n_sel += __popc(coopbits);              // cooperating actions just chosen
+      }
+      fence_proxy_async();  // make out_* visible to the TMA engine
+      __syncthreads();
       if (tid == 0) {
         tma_store_3d(&tm.st_code, out_code, CPAD + c0, r0 + GH, rep);
         tma_store_3d(&tm.st_R, out_R, CPAD + c0, r0 + GH, rep);
         tma_store_3d(&tm.st_S, out_S, (WPAD * 4) + (c0 >> 3), r0 + GH, rep);
         tma_store_commit();
       }
-      // periodic copies other tiles read: ghost columns / ghost rows, edge tiles only
-      const bool edge = tx == 0 || tx == g.n_tx - 1 || (g.wrap_rows && (ty == 0 || ty == g.n_ty - 1));
+      // periodic copies other tiles read: ghost columns / ghost rows, edge tiles only; just the
+      // cells that have copies are visited (store_cell writes the cell and all its copies)
+      const bool ecol0 = tx == 0, ecol1 = tx == g.n_tx - 1;
+      const bool erow0 = g.wrap_rows && ty == 0, erow1 = g.wrap_rows && ty == g.n_ty - 1;
+      const bool edge = ecol0 || ecol1 || erow0 || erow1;
       if (edge) {
         uint8_t *code_out = reinterpret_cast<uint8_t *>(a.code_out) + (long long)rep * g.plane_stride;
         int8_t *R_out = reinterpret_cast<int8_t *>(a.R_out) + (long long)rep * g.plane_stride;
         uint32_t *S_out = a.S_out + (long long)rep * g.bits_stride;
-        for (int e = tid; e < FTR * TC; e += FTHREADS) {
-          const int rr = e >> 7, cc = e & (TC - 1);
-          const int i = r0 + rr, col = c0 + cc;
-          const bool ec = col < GC || col >= g.L - GC;
-          const bool er = g.wrap_rows && (i < GH || i >= g.rows - GH);
-          if (ec || er) {
-            store_cell<uint8_t>(code_out, g, i, col, out_code[e]);
-            store_cell<int8_t>(R_out, g, i, col, out_R[e]);
+        // items 0..2*FTR*GC-1: the GC first / last columns; then 2*GH*TC: the GH first / last rows
+        for (int e = tid; e < 2 * FTR * GC + 2 * GH * TC; e += FTHREADS) {
+          int rr, cc;
+          bool on;
+          if (e < 2 * FTR * GC) {
+            const int side = e >= FTR * GC, q = side ? e - FTR * GC : e;
+            rr = q / GC;
+            cc = side ? TC - GC + (q % GC) : q % GC;
+            on = side ? ecol1 : ecol0;
+          } else {
+            const int q0 = e - 2 * FTR * GC, side = q0 >= GH * TC, q = side ? q0 - GH * TC : q0;
+            rr = side ? FTR - GH + q / TC : q / TC;
+            cc = q % TC;
+            on = side ? erow1 : erow0;
+          }
+          if (on) {
+            const int o = rr * TC + cc;
+            store_cell<uint8_t>(code_out, g, r0 + rr, c0 + cc, out_code[o]);
+            store_cell<int8_t>(R_out, g, r0 + rr, c0 + cc, out_R[o]);
           }
         }
         for (int e = tid; e < FTR * 4; e += FTHREADS) {
@@ -481,10 +598,19 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         __syncthreads();  // out_* is read above; the next tile overwrites it
       }
     }
-    ty = nty; tx = ntx;
+    ty = nty; txs = ntxs; tx = ntx;
   }
-  if (tid == 0 && sel) tma_store_wait_all();
+  if (lane == 0 && (upd || (tid == 0 && sel))) tma_store_wait_all();  // Q segments / tile planes in flight
 
+#ifdef SPGG_TRACE
+  if (tid == 0 && a.trace) {
+    unsigned long long t_end; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long *tr = a.trace + (size_t)blockIdx.x * 4;
+    tr[0] = t_start; tr[1] = t_end; tr[2] = smid; tr[3] = (unsigned long long)tiles_done;
+  }
+#endif
   // ---- per-CTA partial row, then the last CTA of the replica folds them in a fixed order
   double v[NSTAT];
 #pragma unroll

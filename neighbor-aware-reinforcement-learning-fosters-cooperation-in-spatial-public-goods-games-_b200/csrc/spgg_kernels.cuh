@@ -100,6 +100,9 @@ struct KArgs {
   int rel;                 // j - (iteration at start of the spgg_step call)
   int cap;                 // rows per replica in stats/gmax tables
   int do_update, do_select;
+#ifdef SPGG_TRACE
+  unsigned long long *trace;  // debug builds only: per CTA {start ns, end ns, smid, tiles}
+#endif
 };
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -576,9 +579,19 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
       const int sr = rr + HR;
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel && !REPLAY) {
-        // counter = (column group, global row, iteration, 0); one call -> 4 sites
-        philox4x32_10((uint32_t)(((c0 >> 7) << 5) | lane), (uint32_t)(g.row0 + i),
-                      (uint32_t)(a.j + 1), 0u, rc.seed_lo, rc.seed_hi, w4);
+        // counter = (column / 4, global row, iteration, 0): one call serves 4 consecutive sites.
+        // This lane computes the words of columns c0+4*lane..+3; its own sites (columns
+        // c0 + 32*k4 + lane) fetch theirs from lane 8*k4 + lane/4, word lane%4.
+        uint32_t wc[4];
+        philox4x32_10((uint32_t)((c0 >> 2) + lane), (uint32_t)(g.row0 + i),
+                      (uint32_t)(a.j + 1), 0u, rc.seed_lo, rc.seed_hi, wc);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int src = 8 * k4 + (lane >> 2);
+          const uint32_t x0 = __shfl_sync(0xffffffffu, wc[0], src), x1 = __shfl_sync(0xffffffffu, wc[1], src);
+          const uint32_t x2 = __shfl_sync(0xffffffffu, wc[2], src), x3 = __shfl_sync(0xffffffffu, wc[3], src);
+          w4[k4] = sel4<uint32_t>(lane & 3, x0, x1, x2, x3);
+        }
       }
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {

@@ -83,15 +83,14 @@ uint32_t oracle_thr24(double eps) {
   return (uint32_t)t;
 }
 
-/* draw word of site (i,j) at iteration `step`: counter = (group, row, step, 0),
- * group = (j>>7)*32 + (j&31), word index (j>>5)&3 - one Philox call serves the
- * four sites j, j+32, j+64, j+96 of a 128-column segment. */
+/* draw word of site (i,j) at iteration `step`: counter = (j>>2, row, step, 0), word index
+ * j&3 - one Philox call serves four consecutive sites of a row. */
 static inline uint32_t site_word(uint64_t seed, uint32_t step, int i, int j) {
-  uint32_t ctr[4] = {(uint32_t)(((j >> 7) << 5) | (j & 31)), (uint32_t)i, step, 0u};
+  uint32_t ctr[4] = {(uint32_t)(j >> 2), (uint32_t)i, step, 0u};
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t w[4];
   oracle_philox4x32_10(ctr, key, w);
-  return w[(j >> 5) & 3];
+  return w[j & 3];
 }
 
 /* ------------------------------------------------------------ shared bits */
