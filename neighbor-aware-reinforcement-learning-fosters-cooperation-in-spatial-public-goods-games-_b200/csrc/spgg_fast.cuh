@@ -53,13 +53,13 @@ struct FastSmem {
   static constexpr int kOffSt = kOffC + (FTR + 4) * FROWB + FROWB;  // post-action state flags (one guard row after C)
   static constexpr int kOffVal = kOffSt + FTR * FROWB;           // reward floats, rows -M..FTR+M-1
   static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
-  static constexpr int kOffBar = kOffTab + 256 * 4;            // 2 tile barriers + 3 Q barriers per warp
-  static constexpr int kOffFlag = kOffBar + 32 * 8;            // "last CTA" flag
+  static constexpr int kOffBar = kOffTab + 256 * 4;            // 2 tile barriers + kQBufs Q barriers per warp (<= 40)
+  static constexpr int kOffFlag = kOffBar + 40 * 8;            // "last CTA" flag
   static constexpr int kOffRc = kOffFlag + 16;                 // RepConst copy
   static constexpr int kOffRed = (kOffRc + (int)sizeof(RepConst) + 127) / 128 * 128;  // final reduction [8][NSTAT]
   // per warp: kQBufs row segments of 128 float4 (2 KB each), landed by TMA with the 128-byte
   // swizzle (1024-byte aligned) and written back in place
-  static constexpr int kQBufs = 3;
+  static constexpr int kQBufs = 4;
   static constexpr int kQBufBytes = TC * 16;
   static constexpr int kOffQ = (kOffRed + 8 * NSTAT * 8 + 1023) / 1024 * 1024;
   static constexpr int kTotal = kOffQ + (FTHREADS / 32) * kQBufs * kQBufBytes + 1024;  // + base alignment slack
@@ -264,9 +264,13 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     qoff[k] = (lane >> 1) * 128 + ((((lane & 1) * 4 + k) ^ ((lane >> 1) & 7)) << 4);
+  static_assert(FTR == 2 * (FTHREADS / 32), "the Q pipeline assumes two row segments per warp and tile");
   int qb = 0;          // buffer holding the row segment this warp consumes next
   uint32_t qph = 0;    // bit b: parity the next wait on buffer b expects
-  if (lane == 0 && cta < n_tiles) q_issue((tx * TC) >> 3, ty * FTR + warp, 0);
+  if (lane == 0 && cta < n_tiles) {  // both row segments of the first tile
+    q_issue((tx * TC) >> 3, ty * FTR + warp, 0);
+    q_issue((tx * TC) >> 3, ty * FTR + warp + FTHREADS / 32, 1);
+  }
 
   int tiles_done = 0, stage = 0;
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
@@ -290,8 +294,11 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 
     // ---- phase A1: cooperator flags as bytes; one thread expands one staged bit word
     // (32 sites) into 8 words of 4 flag bytes.  Rows -2..FTR+1, staged words 3..8.
-    if (tid < (FTR + 4) * 6) {
-      const int row = tid / 6, bw = tid - row * 6 + 3;
+    // (the upper warps take this, the group statistics below go to warps 2-3: the flat loops
+    // that follow are spread over all warps, so nobody arrives late at the barrier)
+    const int t1 = tid - (FTHREADS - 128);
+    if (t1 >= 0 && t1 < (FTR + 4) * 6) {
+      const int row = t1 / 6, bw = t1 - row * 6 + 3;
       const uint32_t bits = ~st_S[row * (FSROWB / 4) + bw];  // 1 = cooperator
       uint32_t *dst = wC + row * FROWW + (bw - 4) * 8 + 4;
       if (bw == 3) {         // columns -4..-1 only
@@ -356,20 +363,10 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     }
     // ---- phase A4: integer statistics of iteration j straight from the staged words
     if (upd) {
-      for (int e = tid; e < FTR * 32; e += FTHREADS) {
-        const int row = e >> 5, w = (e & 31) + 4;
-        const uint32_t cw = st_code[(row + M) * FROWW + w];
-        const uint32_t Cb = (cw >> 2) & 0x01010101u, Ab = (cw >> 1) & 0x01010101u;  // was-cooperator, cooperates
-        const uint32_t m3 = Cb & Ab, m2 = Cb ^ m3, m1 = Ab ^ m3, m0 = 0x01010101u ^ (Cb | Ab);
-        const uint32_t sn = (cw >> 3) & 0x1F1F1F1Fu;
-        cls_n[0] = __dp4a(m0, 0x01010101u, cls_n[0]); cls_sn[0] = __dp4a(sn, m0, cls_sn[0]);
-        cls_n[1] = __dp4a(m1, 0x01010101u, cls_n[1]); cls_sn[1] = __dp4a(sn, m1, cls_sn[1]);
-        cls_n[2] = __dp4a(m2, 0x01010101u, cls_n[2]); cls_sn[2] = __dp4a(sn, m2, cls_sn[2]);
-        cls_n[3] = __dp4a(m3, 0x01010101u, cls_n[3]); cls_sn[3] = __dp4a(sn, m3, cls_sn[3]);
-      }
       // defectors per 5-site group (spgg.py:586-592), bit-sliced: one thread = 32 sites
-      if (tid < FTR * 4) {
-        const int row = (tid >> 2) + 2, bw = (tid & 3) + 4;
+      const int t2 = tid - 64;
+      if (t2 >= 0 && t2 < FTR * 4) {
+        const int row = (t2 >> 2) + 2, bw = (t2 & 3) + 4;
         const uint32_t *bp = st_S + row * (FSROWB / 4) + bw;
         const uint32_t c = bp[0], u = bp[-(FSROWB / 4)], d = bp[FSROWB / 4];
         const uint32_t l = (c << 1) | (bp[-1] >> 31), r = (c >> 1) | (bp[1] << 31);
@@ -387,17 +384,15 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     const uint8_t *bCode = reinterpret_cast<const uint8_t *>(st_code);
 #pragma unroll 1
     for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
-      // fetch the row segment after this one (same tile, or the first one of this warp's next tile)
+      // fetch the row segment two ahead (the same row of this CTA's next tile) into the buffer
+      // that held the segment two back
       {
-        const bool same_tile = rr + FTHREADS / 32 < FTR;
-        const int nrow = same_tile ? r0 + rr + FTHREADS / 32 : nty * FTR + warp;
-        const int ncol8 = (same_tile ? c0 : ntx * TC) >> 3;
-        int nb = qb + 1;
-        if (nb == SM::kQBufs) nb = 0;
+        int nb = qb + 2;
+        if (nb >= SM::kQBufs) nb -= SM::kQBufs;
         __syncwarp();  // every lane is done with the segment that last used buffer nb
         if (lane == 0) {
           if (upd) tma_store_wait_read_n<1>();  // ... and its tile store has left shared memory
-          if (same_tile || has_next) q_issue(ncol8, nrow, nb);
+          if (has_next) q_issue((ntx * TC) >> 3, nty * FTR + rr, nb);
         }
       }
       uint32_t w4[4] = {0, 0, 0, 0};
@@ -416,6 +411,15 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       const int vb = (rr + M) * FROWB + CPAD + 4 * lane;  // float / byte index of (rr, 4*lane) in the staged planes
       if (upd) {
         codeW = st_code[wo + M * FROWW];
+        {  // integer statistics of iteration j: class = C_old*2 + coop (spgg.py:383,419-420), 4 sites per dp4a
+          const uint32_t Cb = (codeW >> 2) & 0x01010101u, Ab = (codeW >> 1) & 0x01010101u;
+          const uint32_t m3 = Cb & Ab, m2 = Cb ^ m3, m1 = Ab ^ m3, m0 = 0x01010101u ^ (Cb | Ab);
+          const uint32_t sn = (codeW >> 3) & 0x1F1F1F1Fu;
+          cls_n[0] = __dp4a(m0, 0x01010101u, cls_n[0]); cls_sn[0] = __dp4a(sn, m0, cls_sn[0]);
+          cls_n[1] = __dp4a(m1, 0x01010101u, cls_n[1]); cls_sn[1] = __dp4a(sn, m1, cls_sn[1]);
+          cls_n[2] = __dp4a(m2, 0x01010101u, cls_n[2]); cls_sn[2] = __dp4a(sn, m2, cls_sn[2]);
+          cls_n[3] = __dp4a(m3, 0x01010101u, cls_n[3]); cls_sn[3] = __dp4a(sn, m3, cls_sn[3]);
+        }
         const float4 c4 = *reinterpret_cast<const float4 *>(sm_val + vb);
         const float4 u4 = *reinterpret_cast<const float4 *>(sm_val + vb - FROWB);
         const float4 d4 = *reinterpret_cast<const float4 *>(sm_val + vb + FROWB);
@@ -530,6 +534,16 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         const int oo = rr * (TC / 4) + lane;
         reinterpret_cast<uint32_t *>(out_code)[oo] = (SNW << 3) | (CW << 2) | (coopW << 1) | StW;
         reinterpret_cast<uint32_t *>(out_R)[oo] = rnewW;
+        // strategy bits: this lane's 4 coop flags -> nibble; 8 lanes -> one 32-site word (bit = 1: defect)
+        const uint32_t nib = ((coopW * 0x01020408u) >> 24) & 0xFu;
+        uint32_t coopbits = nib << ((lane & 7) * 4);
+        coopbits |= __shfl_xor_sync(0xffffffffu, coopbits, 1);
+        coopbits |= __shfl_xor_sync(0xffffffffu, coopbits, 2);
+        coopbits |= __shfl_xor_sync(0xffffffffu, coopbits, 4);
+        if ((lane & 7) == 0) {
+          out_S[rr * 4 + (lane >> 3)] = ~coopbits;
+          n_sel += __popc(coopbits);  // cooperating actions just chosen
+        }
       }
       if (upd) {
         fence_proxy_async();  // the updated segment becomes visible to the TMA engine
@@ -541,20 +555,9 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       }
       if (++qb == SM::kQBufs) qb = 0;
     }
-    __syncthreads();  // out_code is complete
+    if (sel) fence_proxy_async();  // make out_* visible to the TMA engine
+    __syncthreads();               // everyone is done with this stage, the work planes and out_*
     if (sel) {
-      // strategy bits of the tile from the coop flags in out_code: one thread = one 32-site word
-      if (tid < FTR * 4) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(out_code) + tid * 2;
-        const uint4 lo = src[0], hi = src[1];
-        auto nib = [](uint32_t w) { return ((((w >> 1) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; };
-        const uint32_t coopbits = nib(lo.x) | (nib(lo.y) << 4) | (nib(lo.z) << 8) | (nib(lo.w) << 12) |
-                                  (nib(hi.x) << 16) | (nib(hi.y) << 20) | (nib(hi.z) << 24) | (nib(hi.w) << 28);
-        out_S[tid] = ~coopbits;                 // bit = 1: defect
-        n_sel += __popc(coopbits);              // cooperating actions just chosen
-      }
-      fence_proxy_async();  // make out_* visible to the TMA engine
-      __syncthreads();
       if (tid == 0) {
         tma_store_3d(&tm.st_code, out_code, CPAD + c0, r0 + GH, rep);
         tma_store_3d(&tm.st_R, out_R, CPAD + c0, r0 + GH, rep);
