@@ -128,6 +128,10 @@ static void build_repconst(const spgg_params_t &p, RepConst *rc) {
   int8_quantum(p, &rc->rq, &rc->gain_i, &rc->loss_i, &rc->rmin_i, &rc->rmax_i);
   rc->seed_lo = (uint32_t)p.seed;
   rc->seed_hi = (uint32_t)(p.seed >> 32);
+  for (uint32_t r = 0; r < 10; ++r) {
+    rc->pkeys[2 * r] = rc->seed_lo + r * 0x9E3779B9u;
+    rc->pkeys[2 * r + 1] = rc->seed_hi + r * 0xBB67AE85u;
+  }
   rc->has_ratio = (rc->wR != 0.0);
   for (int code = 0; code < 128; ++code) {
     const int sn = code >> 2, C = (code >> 1) & 1, coop = code & 1;

@@ -213,7 +213,6 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   const float alpha = rc.alpha_f, gamma = rc.gamma_f, kappa = rc.kappa_f;
   const int gain_i = rc.gain_i, loss_i = rc.loss_i, rmin_i = rc.rmin_i, rmax_i = rc.rmax_i;
   const bool has_ratio = rc.has_ratio != 0;
-  const uint32_t seed_lo = rc.seed_lo, seed_hi = rc.seed_hi;
 
   // per-thread statistics: exact 32-bit integer counters + fp32 partial sums.
   // class = C_old*2 + coop (spgg.py:383,419-420)
@@ -398,8 +397,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel) {
         // counter = (column / 4, global row, iteration, 0); one call -> this lane's 4 sites
-        philox4x32_10((uint32_t)((c0 >> 2) + lane), (uint32_t)(g.row0 + r0 + rr),
-                      (uint32_t)(a.j + 1), 0u, seed_lo, seed_hi, w4);
+        philox4x32_10_keys((uint32_t)((c0 >> 2) + lane), (uint32_t)(g.row0 + r0 + rr),
+                           (uint32_t)(a.j + 1), 0u, s_rc.pkeys, w4);
       }
       const int wo = rr * FROWW + (CPAD / 4) + lane;      // word of (rr, 4*lane) in a tile-row-indexed plane
       const uint32_t RW = st_R[wo + M * FROWW];
@@ -443,15 +442,31 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       unsigned char *qbuf = sQ + qb * SM::kQBufBytes;
       mbar_wait(&qbar[qb], (qph >> qb) & 1u);
       qph ^= 1u << qb;
+      // The four Q entries of a site stay in the landed segment: the entry being updated and
+      // the row of the next state are addressed there (load/store pipe) instead of being
+      // selected in registers - the integer/select pipe is the busy one in this loop.
+      // Stages (all loads of a stage before the stores of the next, for all four sites):
+      //   1 gather   2 arithmetic   3 write Q[s][a]   4 re-read the updated entries: statistics, greedy action
       uint32_t coopW = 0, rnewW = 0;
+      float qfin[4];
+      int eidx[4];
+      if (upd) {
+        float qe[4], na[4], nb_[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 qv = *reinterpret_cast<const float4 *>(qbuf + qoff[k]);
-        float q0_ = qv.x, q1_ = qv.y, q2_ = qv.z, q3_ = qv.w;
-        const int s_new = (StW >> (8 * k)) & 1u;
-        if (upd) {
+        for (int k = 0; k < 4; ++k) {
+          const float *qs = reinterpret_cast<const float *>(qbuf + qoff[k]);
           const uint32_t code = (codeW >> (8 * k)) & 0xFFu;
-          const int s = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
+          const int s_new = (StW >> (8 * k)) & 1u;
+          eidx[k] = (int)(((code & 1u) << 1) | (((code >> 1) & 1u) ^ 1u));  // index of Q[s][a], a = !coop
+          qe[k] = qs[eidx[k]];
+          const float2 nrow = *reinterpret_cast<const float2 *>(qs + 2 * s_new);  // pre-update row of s'
+          na[k] = nrow.x; nb_[k] = nrow.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t code = (codeW >> (8 * k)) & 0xFFu;
+          const int s = code & 1u, coop = (code >> 1) & 1u;
+          const int s_new = (StW >> (8 * k)) & 1u;
           const float vx = vc[k];
           // neighbour-aware term inputs: spgg.py:486-494, offsets in the order of spgg.py:479-485
           // ((dx,dy) names the site (i-dx, j-dy)); the first arg-max wins
@@ -480,38 +495,41 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
             if (d > best) { best = d; boff = no[q]; second = (q >= 4); }
           }
           const bool same = (((bCode[vb + k + boff] >> 1) & 1u) == (unsigned)coop);
-          const int ee = 2 * s + (coop ^ 1);  // index of Q[s][a], a = !coop
-          const float qe = sel4<float>(ee, q0_, q1_, q2_, q3_);
-          const float na = s_new ? q2_ : q0_, nb_ = s_new ? q3_ : q1_;  // pre-update row of s'
-          const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na, nb_), vx), qe);  // algorithms.py:128
-          const float qtd = __fmaf_rn(alpha, td, qe);                            // algorithms.py:131
-          const float lam = __fmul_rn(__fmul_rn(kappa, fmaxf(0.0f, best)), inv_den);  // spgg.py:489
-          const float nu = same ? lam : -lam;                                    // spgg.py:494-495
+          const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na[k], nb_[k]), vx), qe[k]);  // algorithms.py:128
+          const float qtd = __fmaf_rn(alpha, td, qe[k]);                                   // algorithms.py:131
+          const float lam = __fmul_rn(__fmul_rn(kappa, fmaxf(0.0f, best)), inv_den);       // spgg.py:489
+          const float nu = same ? lam : -lam;                                              // spgg.py:494-495
           // TD error on the table after the TD write (spgg.py:446-473), for the NI statistic
           const bool hit = (s_new == s);
-          const float na2 = (hit && coop) ? qtd : na;
-          const float nb2 = (hit && !coop) ? qtd : nb_;
+          const float na2 = (hit && coop) ? qtd : na[k];
+          const float nb2 = (hit && !coop) ? qtd : nb_[k];
           const float td2 = __fsub_rn(__fmaf_rn(gamma, fmaxf(na2, nb2), vx), qtd);
-          const float qfin = __fadd_rn(qtd, nu);                                 // spgg.py:509
+          qfin[k] = __fadd_rn(qtd, nu);                                                    // spgg.py:509
           const float an = fabsf(nu);
           s_ni += __fdividef(an, fabsf(alpha * td2) + an + 1e-8f);               // x100 at the fold; spgg.py:512
-          q0_ = (ee == 0) ? qfin : q0_;
-          q1_ = (ee == 1) ? qfin : q1_;
-          q2_ = (ee == 2) ? qfin : q2_;
-          q3_ = (ee == 3) ? qfin : q3_;
           if (has_ratio) s_ratio += sm_ratio[code >> 1];  // zero for defecting codes
           if (best > 0.f) pk_best += second ? 0x10001u : 1u;
-          const float m = wasC ? 1.0f : 0.0f;
-          sq0 += q0_; sq1 += q1_; sq2 += q2_; sq3 += q3_;
-          sc0 = fmaf(m, q0_, sc0); sc1 = fmaf(m, q1_, sc1); sc2 = fmaf(m, q2_, sc2); sc3 = fmaf(m, q3_, sc3);
-          *reinterpret_cast<float4 *>(qbuf + qoff[k]) = make_float4(q0_, q1_, q2_, q3_);
         }
-        if (sel) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) reinterpret_cast<float *>(qbuf + qoff[k])[eidx[k]] = qfin[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 qn = *reinterpret_cast<const float4 *>(qbuf + qoff[k]);   // after both updates
+          const float m = ((codeW >> (8 * k + 2)) & 1u) ? 1.0f : 0.0f;           // was a cooperator
+          sq0 += qn.x; sq1 += qn.y; sq2 += qn.z; sq3 += qn.w;                    // spgg.py:562-583
+          sc0 = fmaf(m, qn.x, sc0); sc1 = fmaf(m, qn.y, sc1); sc2 = fmaf(m, qn.z, sc2); sc3 = fmaf(m, qn.w, sc3);
+        }
+      }
+      if (sel) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int s_new = (StW >> (8 * k)) & 1u;
+          const float2 grow = *reinterpret_cast<const float2 *>(
+              reinterpret_cast<const float *>(qbuf + qoff[k]) + 2 * s_new);      // Q[s'] after the update
           const bool explore = (w4[k] >> 8) < thr;
           const int rnd = (int)(w4[k] & 1u);
-          const float ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
-          const int greedy = (gb > ga) ? 1 : 0;      // np.argmax, tie -> 0   algorithms.py:107
-          const int a_new = explore ? rnd : greedy;  // algorithms.py:109
+          const int greedy = (grow.y > grow.x) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
+          const int a_new = explore ? rnd : greedy;      // algorithms.py:109
           const int r_old = (int)(int8_t)(RW >> (8 * k));
           int t = r_old + (a_new == 0 ? gain_i : -loss_i);  // spgg.py:321-323
           t = min(max(t, rmin_i), rmax_i);
