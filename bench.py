@@ -30,6 +30,17 @@ C4 = dict(r=3.0, c=1, cost=1, alpha=0.8, gamma=0.9, epsilon=0.5, epsilon_decay=0
           rep_gain_C=1.0, state_representation="reputation")
 
 
+def ncu_traffic(L):
+    """DRAM bytes per k_step launch from the committed `ncu --set full` capture
+    (profiles/k_step_traffic.json, written by scripts/make_profile_summary.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_step_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["traffic_bytes_per_launch"]) if int(d.get("L", 0)) == int(L) else None
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -269,7 +280,9 @@ def main():
     t_step = float(np.mean([b.elapsed_time(c) for a, b, c in evs[:-1]])) * 1e-3
     achieved = BYTES_PER_SITE_FP32 * n_sites / t_step / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "k_step<ModeF32I8,1,rep,philox>",
+                "frac": achieved / peak, "traffic": ncu_traffic(L),
+                "kernel": "k_step_fast<M=1, reputation, update+select> (fused SPGG iteration)",
+                "algorithmic_bytes_per_launch": BYTES_PER_SITE_FP32 * n_sites,
                 "kernel_us": t_step * 1e6, "gmax_kernel_us": t_gmax * 1e6,
                 "algorithmic_bytes_per_site": BYTES_PER_SITE_FP32, "peak_source": peak_src,
                 "whole_step_frac": BYTES_PER_SITE_FP32 * value / 1e9 / peak}

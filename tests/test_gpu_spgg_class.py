@@ -1,0 +1,116 @@
+"""The drop-in class on the GPU: ``SPGG(**params).run(h5)`` against the golden runs of the
+executed reference (same call pattern as src/experiments/runner.py:88-105)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import C1, C2, RUNNER_FIXED, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["c1_rep_m1", "c2_act_m2", "rep_m2_r36", "act_m1_k0", "ctor_defaults", "odd_L_fracR"]
+
+
+def _read(path):
+    from spgg_b200 import h5lite
+    with h5lite.open_file(path, "r") as f:
+        return {k: np.array(f[k]) for k in f.keys()}
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_run_replays_the_reference_bit_for_bit(tmp_path, golden_dir, name):
+    """precision='fp64', draws='numpy', seed=<the golden's seed>: the class consumes the same
+    NumPy stream as the reference (ctor: uniform Q then randint S; per step rand then
+    randint) and must reproduce its files: every dataset name/dtype/shape, S/R/Q bit for bit."""
+    import spgg_b200
+    z, p = load_golden(golden_dir, name)
+    m = spgg_b200.SPGG(**p, seed=int(z["seed"]), precision="fp64", draws="numpy")
+    assert np.array_equal(m.q_table, z["q0"]) and np.array_equal(m._Sn, z["s0"])
+    m.folder = str(tmp_path)
+    path = str(tmp_path / "run.h5")
+    ret = m.run(path)
+    assert os.path.isdir(tmp_path / "plots" / "snapshots")          # spgg.py:365-366
+    assert np.array_equal(m._Sn, z["s_final"]) and m._Sn.dtype == np.int64
+    assert np.array_equal(m.R, z["r_final"])
+    assert np.array_equal(m.q_table, z["q_final"])
+    np.testing.assert_allclose(ret, z["ret"], rtol=1e-12)
+    got = _read(path)
+    shapes = json.loads(str(z["dataset_shapes"]))
+    assert sorted(got) == sorted(shapes)                             # the full dataset contract
+    for k, (dt, shp) in shapes.items():
+        assert str(got[k].dtype) == dt and list(got[k].shape) == shp, k
+    for k in [f[3:] for f in z.files if f.startswith("ds_")]:
+        want = z["ds_" + k]
+        if want.dtype.kind == "i":
+            assert np.array_equal(got[k], want), k
+        else:
+            np.testing.assert_allclose(got[k], want, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+    assert m.kernel_launches > 0
+    assert m.epsilon == pytest.approx(float(got["epsilon_history_final"][-1]))
+
+
+def test_runner_call_pattern_default_mode(tmp_path):
+    """runner.py:88-105 verbatim (shorter run): throughput mode, Philox draws, snapshots at the
+    reference's iterations, series lengths, value ranges."""
+    import spgg_b200
+    spgg = spgg_b200.SPGG(
+        r=3.0, c=1, cost=1, iterations=1200, L=100, num_of_strategies=2, K=0.1, population_type=0,
+        alpha=0.8, gamma=0.9, epsilon=0.5, epsilon_decay=0.99, epsilon_min=0.01,
+        influence_factor=1.0, use_second_order=False, lambda_epsilon=0.01,
+        delta_R_C=1, delta_R_D=1, R_min=-10, R_max=10, reward_weight_payoff=0.95, rep_gain_C=1.0,
+        state_representation="reputation", algorithm="qlearning")
+    spgg.folder = str(tmp_path)
+    record = spgg.run(str(tmp_path / "experiment_data.h5"))
+    final_coop_ratio, final_def_ratio, _ = record
+    assert 0 <= final_coop_ratio <= 1 and abs(final_coop_ratio + final_def_ratio - 1) < 1e-12
+    final_rep_mean = spgg.rep_avg_history[-1] if spgg.rep_avg_history else 0   # runner.py:108
+    assert final_rep_mean == 0
+    d = _read(str(tmp_path / "experiment_data.h5"))
+    T = 1200
+    for k in ("coop_rate_history", "neighbor_influence_percent", "switch_C_to_D", "avg_q_s1_d_history"):
+        assert d[k].shape == (T,)
+    for i in (1, 10, 100, 1000):
+        assert d[f"R_snapshot_{i}"].shape == (100, 100) and d[f"Sn_snapshot_{i}"].dtype == np.int64
+        assert d[f"rep_hist_{i}"].sum() == 100 * 100
+    assert "R_snapshot_5000" not in d
+    assert np.array_equal(d["R_snapshot_1"], np.zeros((100, 100)))
+    assert d["Sn_final"].dtype == np.int64 and set(np.unique(d["Sn_final"])) <= {0, 1}
+    assert d["coop_rate_history"][-1] == pytest.approx((spgg._Sn == 0).mean(), abs=0.05)
+    assert d["cluster_sizes"].sum() == (d["Sn_final"] == 0).sum()
+    assert d["epsilon_history_final"][-1] == 0.01
+    assert np.all((d["group_comp_d0_history"] >= 0) & (d["group_comp_d0_history"] <= 100))
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2"])
+def test_philox_stream_stays_in_the_reference_seed_band(golden_dir, cfg):
+    """north_star: with the native Philox stream the long-run cooperation-rate curve must fall
+    within the reference's seed-to-seed band (8 reference seeds, L=200, 1000 iterations;
+    band = mean +- max(4 sd, 0.02) at t = 100, 300, 1000)."""
+    import spgg_b200
+    z = np.load(os.path.join(golden_dir, f"band_{cfg}.npz"))
+    p = json.loads(str(z["params_json"]))
+    curves = z["coop_rate_history"].astype(np.float64)
+    mean, sd = curves.mean(0), curves.std(0)
+    T = curves.shape[1]
+    for seed in (1, 2, 3):
+        eng = spgg_b200.Engine(p, seeds=seed, precision="fp32")
+        rs = np.random.RandomState(seed)
+        L = p["L"]
+        eng.set_state(rs.randint(0, 2, (L, L)), np.zeros((L, L)), rs.uniform(-0.01, 0.01, (L, L, 2, 2)))
+        eng.step(T)
+        rows = eng.stats()[1:]
+        fc = rows[:, 0] / (L * L)
+        for t in (99, 299, 999):
+            tol = max(4 * sd[t], 0.02)
+            assert abs(fc[t] - mean[t]) <= tol, (cfg, seed, t, fc[t], mean[t], sd[t])
+        eng.close()
+
+
+def test_other_td_rules_fail_loudly(tmp_path):
+    import spgg_b200
+    for algo in ("sarsa", "expected_sarsa", "double_qlearning"):
+        m = spgg_b200.SPGG(L=16, iterations=3, algorithm=algo, seed=1)
+        with pytest.raises(ValueError, match="no CPU fallback"):
+            m.run(str(tmp_path / "x.h5"))
