@@ -50,6 +50,7 @@ struct spgg_handle {
   std::vector<RepConst> rc_host;
   Geom g{};
   int threads = 256;
+  int gmax_ctas = 1;  // CTAs per replica of k_gmax_fast
   size_t smem_step = 0, smem_gmax = 0;
   // device memory
   RepConst *d_rc = nullptr;
@@ -349,6 +350,11 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     fast_fn_t ff = pick_fast(h->M, h->action, 1, 1);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff, FTHREADS, fast_smem(h->M)));
     CUDA_TRY(cudaFuncSetAttribute(pick_gfast(h->M), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfast_smem(h->M)));
+    int gocc = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, pick_gfast(h->M), GWARPS * 32, gfast_smem(h->M)));
+    const long long n_tiles_g = (long long)((p0.L + TC - 1) / TC) * (p0.rows / FTR);
+    h->gmax_ctas = (int)std::max<long long>(1, std::min<long long>((n_tiles_g + GWARPS - 1) / GWARPS,
+                       ((long long)prop.multiProcessorCount * std::max(1, gocc)) / n_replicas));
   }
   CUDA_TRY(cudaFuncSetAttribute(pick_gmax(h->mode, h->M), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)h->smem_gmax));
@@ -689,7 +695,7 @@ extern "C" int spgg_phase_gmax(spgg_t *h, void *stream_) {
   a.stop_at = h->d_stop;
   a.j = (int)(h->pend_t0 + h->pend_rel); a.rel = h->pend_rel; a.cap = h->cap;
   if (h->fast) {
-    pick_gfast(h->M)<<<h->g.ctas_per_rep * h->n_rep, FTHREADS, gfast_smem(h->M), st>>>(h->fmaps[h->cur].ld_code, a);
+    pick_gfast(h->M)<<<h->gmax_ctas * h->n_rep, GWARPS * 32, gfast_smem(h->M), st>>>(h->fmaps[h->cur].ld_code, a);
   } else {
     gmax_fn_t f = pick_gmax(h->mode, h->M);
     f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_gmax, st>>>(a);

@@ -709,83 +709,103 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   step_fast_body<M, ACTION, UPD, SEL>(tm, a);
 }
 
-// lattice-global max |reward difference| of iteration j (spgg.py:486-488), fast path: the code
-// tile + halo is staged by TMA, rewards are looked up 4 codes per thread, and every unordered
-// neighbour pair is visited once (the offset set is symmetric, |d| too).
+// lattice-global max |reward difference| of iteration j (spgg.py:486-488), fast path.
+// Warp-autonomous: every warp walks its own 16x128-site tiles (TMA-staged code tile + halo,
+// double-buffered per warp), top row to bottom row, a lane holding the rewards of 4 consecutive
+// sites of the current and the previous row(s) in registers; rewards come from a reward table
+// replicated 32 times (entry c of lane l at [c*32 + l]: conflict-free).  Every unordered
+// neighbour pair is visited once (the offset set is symmetric, |d| too):
+//   M=1: (1,0) (0,1)        M=2: + (2,0) (0,2) (1,1) (1,-1)
+// No block-wide barrier after the prologue.
+constexpr int GWARPS = 8;  // warps per CTA of k_gmax_fast
 template <int M>
 struct GmaxSmem {
   static constexpr int kRowsCR = FTR + 2 * M;
   static constexpr int kStageBytes = (kRowsCR * FROWB + 127) / 128 * 128;
-  static constexpr int kOffVal = 2 * kStageBytes;
-  static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
-  static constexpr int kOffBar = kOffTab + 128 * 4;
-  static constexpr int kTotal = kOffBar + 64;
+  static constexpr int kOffTab = GWARPS * 2 * kStageBytes;       // 128 x 32 floats
+  static constexpr int kOffBar = kOffTab + 128 * 32 * 4;         // 2 barriers per warp
+  static constexpr int kTotal = kOffBar + GWARPS * 2 * 8 + 128;  // + base alignment slack
 };
 
 template <int M>
-__global__ void __launch_bounds__(FTHREADS, 4)
+__global__ void __launch_bounds__(GWARPS * 32, 3)
 k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
   typedef GmaxSmem<M> SM;
   const Geom &g = a.g;
-  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  const int ctas = gridDim.x / g.n_rep;
+  const int rep = blockIdx.x / ctas, cta = blockIdx.x - rep * ctas;
   const int stop = a.stop_at[rep];
   if (stop >= 0 && a.j > stop) return;
   extern __shared__ __align__(128) unsigned char smem_gfast[];
-  unsigned char *smem = smem_gfast;
-  float *sm_val = reinterpret_cast<float *>(smem + SM::kOffVal);
-  float *sm_tab = reinterpret_cast<float *>(smem + SM::kOffTab);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kOffBar);
-  __shared__ float s_wmax[FTHREADS / 32];
+  unsigned char *smem = smem_gfast + ((128u - (smem_u32(smem_gfast) & 127u)) & 127u);
+  float *tab32 = reinterpret_cast<float *>(smem + SM::kOffTab);
+  __shared__ float s_wmax[GWARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 128) sm_tab[tid] = a.rc[rep].rewtab[tid];
-  if (tid == 0) {
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kOffBar) + warp * 2;
+  unsigned char *stg = smem + warp * (2 * SM::kStageBytes);
+  for (int i = tid; i < 128 * 32; i += GWARPS * 32) tab32[i] = a.rc[rep].rewtab[i >> 5];
+  if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const float *tl = tab32 + lane;
   const int n_tiles = g.n_tx * g.n_ty;
+  const int gw = cta * GWARPS + warp, n_gw = ctas * GWARPS;
   auto issue = [&](int tile, int st) {
     const int r0 = (tile / g.n_tx) * FTR, c0 = (tile % g.n_tx) * TC;
     mbar_expect_tx(&bars[st], SM::kRowsCR * FROWB);
-    tma_load_3d(smem + st * SM::kStageBytes, &ld_code, &bars[st], c0, r0 + GH - M, rep);
+    tma_load_3d(stg + st * SM::kStageBytes, &ld_code, &bars[st], c0, r0 + GH - M, rep);
   };
-  if (tid == 0 && cta < n_tiles) issue(cta, 0);
+  if (lane == 0 && gw < n_tiles) issue(gw, 0);
   float lmax = 0.f;
-  int tiles_done = 0, stage = 0;
-  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
-    if (tid == 0 && tile + g.ctas_per_rep < n_tiles) issue(tile + g.ctas_per_rep, stage ^ 1);
-    mbar_wait(&bars[stage], (uint32_t)(tiles_done >> 1) & 1u);
-    const uint32_t *st_code = reinterpret_cast<const uint32_t *>(smem + stage * SM::kStageBytes);
-    for (int e = tid; e < SM::kRowsCR * FROWW; e += FTHREADS) {
-      const uint32_t cw = st_code[e];
-      float4 v;
-      v.x = sm_tab[(cw >> 1) & 0x7Fu];
-      v.y = sm_tab[(cw >> 9) & 0x7Fu];
-      v.z = sm_tab[(cw >> 17) & 0x7Fu];
-      v.w = sm_tab[(cw >> 25) & 0x7Fu];
-      *reinterpret_cast<float4 *>(sm_val + e * 4) = v;
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
-      const int rb = (rr + M) * FROWB + CPAD + lane;
+  auto upd = [&](float x, float y) { lmax = fmaxf(lmax, fabsf(__fsub_rn(x, y))); };
+  int done = 0, stage = 0;
+  for (int tile = gw; tile < n_tiles; tile += n_gw, ++done, stage ^= 1) {
+    __syncwarp();  // every lane has left the stage about to be refilled
+    if (lane == 0 && tile + n_gw < n_tiles) issue(tile + n_gw, stage ^ 1);
+    mbar_wait(&bars[stage], (uint32_t)(done >> 1) & 1u);
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(stg + stage * SM::kStageBytes) + (CPAD / 4);
+    float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f};  // rewards one / two rows up
+    float u1l = 0.f, u1r = 0.f;                                        // ... and their row-neighbours
+#pragma unroll 2
+    for (int s = 0; s < FTR + M; ++s) {  // staged row s = tile row s - M
+      const uint32_t w = cw[s * FROWW + lane];
+      const uint32_t wl = cw[s * FROWW - 1];         // columns -4..-1 (same word for every lane)
+      float c[4];
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const int crow = rb + 32 * k4;
-        const float vx = sm_val[crow];
-        // one representative of every +/- offset pair: (1,0) (0,1) | (2,0) (0,2) (1,1) (1,-1)
-        lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - FROWB], vx)));
-        lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - 1], vx)));
-        if constexpr (M == 2) {
-          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - 2 * FROWB], vx)));
-          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - 2], vx)));
-          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - FROWB - 1], vx)));
-          lmax = fmaxf(lmax, fabsf(__fsub_rn(sm_val[crow - FROWB + 1], vx)));
+      for (int k = 0; k < 4; ++k) c[k] = tl[((w >> (8 * k + 1)) & 0x7Fu) << 5];
+      float l1 = __shfl_up_sync(0xffffffffu, c[3], 1);
+      const float hl1 = tl[((wl >> 25) & 0x7Fu) << 5];
+      if (lane == 0) l1 = hl1;
+      float l2 = 0.f, r1 = 0.f;
+      if constexpr (M == 2) {
+        l2 = __shfl_up_sync(0xffffffffu, c[2], 1);
+        const float hl2 = tl[((wl >> 17) & 0x7Fu) << 5];
+        if (lane == 0) l2 = hl2;
+        const uint32_t wr = cw[s * FROWW + 32];      // columns 128..131
+        r1 = __shfl_down_sync(0xffffffffu, c[0], 1);
+        const float hr1 = tl[((wr >> 1) & 0x7Fu) << 5];
+        if (lane == 31) r1 = hr1;
+      }
+      if (s >= M) {  // a row of the tile: pairs with the rows above and to the left
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          upd(u1[k], c[k]);                                   // (1,0)
+          upd(k == 0 ? l1 : c[(k + 3) & 3], c[k]);            // (0,1)
+          if constexpr (M == 2) {
+            upd(u2[k], c[k]);                                 // (2,0)
+            upd(k == 0 ? l2 : (k == 1 ? l1 : c[(k + 2) & 3]), c[k]);   // (0,2)
+            upd(k == 0 ? u1l : u1[(k + 3) & 3], c[k]);        // (1,1)
+            upd(k == 3 ? u1r : u1[(k + 1) & 3], c[k]);        // (1,-1)
+          }
         }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { u2[k] = u1[k]; u1[k] = c[k]; }
+      u1l = l1; u1r = r1;
     }
-    __syncthreads();  // the value plane and this stage are free again
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_down_sync(0xffffffffu, lmax, o));
@@ -793,7 +813,7 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
   __syncthreads();
   if (tid == 0) {
     float m = s_wmax[0];
-    for (int w = 1; w < FTHREADS / 32; ++w) m = fmaxf(m, s_wmax[w]);
+    for (int w = 1; w < GWARPS; ++w) m = fmaxf(m, s_wmax[w]);
     // non-negative IEEE floats order like unsigned integers
     atomicMax(reinterpret_cast<unsigned int *>(a.gmax) + (long long)rep * a.cap + a.rel, __float_as_uint(m));
   }
