@@ -180,6 +180,25 @@ static size_t step_smem(int mode, int TR) {
   }
 }
 
+// launch with programmatic stream serialization (the fast kernels call griddepcontrol.wait
+// before touching anything an earlier kernel wrote); SPGG_NO_PDL=1 falls back to plain launches
+template <class... KArgsT, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgsT...), int grid, int block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  static const bool use_pdl = getenv("SPGG_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ---------------------------------------------------------------- fast path plumbing
 typedef void (*fast_fn_t)(const FastMaps, KArgs);
 template <int M, bool ACTION>
@@ -671,7 +690,7 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   if (h->fast && !replay) {
     if (!do_update && !do_select) return SPGG_OK;
     fast_fn_t ff = pick_fast(h->M, h->action, do_update, do_select);
-    ff<<<h->g.ctas_per_rep * h->n_rep, FTHREADS, fast_smem(h->M), st>>>(h->fmaps[h->cur], a);
+    CUDA_TRY(launch_pdl(ff, h->g.ctas_per_rep * h->n_rep, FTHREADS, fast_smem(h->M), st, h->fmaps[h->cur], a));
   } else {
     step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
     f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_step, st>>>(a);
@@ -695,7 +714,8 @@ extern "C" int spgg_phase_gmax(spgg_t *h, void *stream_) {
   a.stop_at = h->d_stop;
   a.j = (int)(h->pend_t0 + h->pend_rel); a.rel = h->pend_rel; a.cap = h->cap;
   if (h->fast) {
-    pick_gfast(h->M)<<<h->gmax_ctas * h->n_rep, GWARPS * 32, gfast_smem(h->M), st>>>(h->fmaps[h->cur].ld_code, a);
+    CUDA_TRY(launch_pdl(pick_gfast(h->M), h->gmax_ctas * h->n_rep, GWARPS * 32, gfast_smem(h->M), st,
+                        h->fmaps[h->cur].ld_code, a));
   } else {
     gmax_fn_t f = pick_gmax(h->mode, h->M);
     f<<<h->g.ctas_per_rep * h->n_rep, h->threads, h->smem_gmax, st>>>(a);

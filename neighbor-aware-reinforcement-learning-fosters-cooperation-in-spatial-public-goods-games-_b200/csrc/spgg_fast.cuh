@@ -141,6 +141,10 @@ __device__ __forceinline__ void tma_store_wait_read_n() {
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// programmatic dependent launch: let the next kernel of the stream be scheduled while this one
+// drains, and wait (in the next kernel) until everything before it has completed and is visible
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // bytes of the column-shifted neighbours of a 4-site word
@@ -699,6 +703,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 template <int M, bool ACTION, bool UPD, bool SEL>
 __global__ void __launch_bounds__(FTHREADS, SPGG_FAST_MINBLOCKS)
 k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();  // the planes, the stop flags and gmax come from the kernels before this one
   const int rep = blockIdx.x / a.g.ctas_per_rep;
   const int stop = a.stop_at[rep];
   if (stop >= 0 && a.j > stop) return;
@@ -734,8 +740,7 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
   const Geom &g = a.g;
   const int ctas = gridDim.x / g.n_rep;
   const int rep = blockIdx.x / ctas, cta = blockIdx.x - rep * ctas;
-  const int stop = a.stop_at[rep];
-  if (stop >= 0 && a.j > stop) return;
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem_gfast[];
   unsigned char *smem = smem_gfast + ((128u - (smem_u32(smem_gfast) & 127u)) & 127u);
   float *tab32 = reinterpret_cast<float *>(smem + SM::kOffTab);
@@ -743,12 +748,24 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kOffBar) + warp * 2;
   unsigned char *stg = smem + warp * (2 * SM::kStageBytes);
-  for (int i = tid; i < 128 * 32; i += GWARPS * 32) tab32[i] = a.rc[rep].rewtab[i >> 5];
+  __shared__ float s_tab[128];
+  if (tid < 128) s_tab[tid] = a.rc[rep].rewtab[tid];  // one global load per thread, then replicate on chip
   if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  pdl_wait();  // the code plane and the stop flags come from the k_step before this kernel
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  if (lane == 0 && cta * GWARPS + warp < g.n_tx * g.n_ty) {  // first tile on its way while the table is built
+    const int t0 = cta * GWARPS + warp;
+    mbar_expect_tx(&bars[0], SM::kRowsCR * FROWB);
+    tma_load_3d(stg, &ld_code, &bars[0], (t0 % g.n_tx) * TC, (t0 / g.n_tx) * FTR + GH - M, rep);
+  }
+#pragma unroll 4
+  for (int i = tid; i < 128 * 32; i += GWARPS * 32) tab32[i] = s_tab[i >> 5];
   __syncthreads();
   const float *tl = tab32 + lane;
   const int n_tiles = g.n_tx * g.n_ty;
@@ -758,7 +775,6 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
     mbar_expect_tx(&bars[st], SM::kRowsCR * FROWB);
     tma_load_3d(stg + st * SM::kStageBytes, &ld_code, &bars[st], c0, r0 + GH - M, rep);
   };
-  if (lane == 0 && gw < n_tiles) issue(gw, 0);
   float lmax = 0.f;
   auto upd = [&](float x, float y) { lmax = fmaxf(lmax, fabsf(__fsub_rn(x, y))); };
   int done = 0, stage = 0;
