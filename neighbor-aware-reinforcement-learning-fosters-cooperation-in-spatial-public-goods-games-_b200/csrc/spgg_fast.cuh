@@ -50,8 +50,7 @@ struct FastSmem {
   // work planes, all with the staged row geometry (row r, word w <-> tile cols 4(w-4)..4(w-4)+3),
   // one guard row before the first so flat stencils may read one word before a plane
   static constexpr int kOffC = kOutS + 256 + FROWB;              // cooperator flags, rows -2..FTR+1
-  static constexpr int kOffSt = kOffC + (FTR + 4) * FROWB + FROWB;  // post-action state flags (one guard row after C)
-  static constexpr int kOffVal = kOffSt + FTR * FROWB;           // reward floats, rows -M..FTR+M-1
+  static constexpr int kOffVal = kOffC + (FTR + 4) * FROWB + FROWB;  // reward floats, rows -M..FTR+M-1 (one guard row after C)
   static constexpr int kOffTab = kOffVal + kRowsCR * FROWB * 4;
   static constexpr int kOffBar = kOffTab + 256 * 4;            // 2 tile barriers + kQBufs Q barriers per warp (<= 40)
   static constexpr int kOffFlag = kOffBar + 40 * 8;            // "last CTA" flag
@@ -175,7 +174,6 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   // the swizzled Q buffers need a 1024-byte aligned base; kTotal carries the slack
   unsigned char *smem = smem_fast + ((1024u - (smem_u32(smem_fast) & 1023u)) & 1023u);
   uint32_t *wC = reinterpret_cast<uint32_t *>(smem + SM::kOffC);
-  uint32_t *wSt = reinterpret_cast<uint32_t *>(smem + SM::kOffSt);
   float *sm_val = reinterpret_cast<float *>(smem + SM::kOffVal);
   float *sm_tab = reinterpret_cast<float *>(smem + SM::kOffTab);
   float *sm_ratio = sm_tab + 128;
@@ -334,36 +332,6 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         *reinterpret_cast<float4 *>(sm_val + e * 4) = v;
       }
     }
-    // ---- phase A3: post-action reputation state (spgg.py:292-307) for the tile, 4 sites per
-    // word: v = R + 16 in each byte (|R| <= 15 is a launch precondition); sum v > 16 n <=> sum R > 0
-    if (!ACTION) {
-      for (int e = tid; e < FTR * 32; e += FTHREADS) {
-        const int row = e >> 5, w = (e & 31) + 4;
-        const uint32_t *rp = st_R + (row + M) * FROWW + w;
-        auto bias = [](uint32_t x) { return (x ^ 0x10101010u) & 0x1F1F1F1Fu; };
-        const uint32_t c = bias(rp[0]), l = bias(rp[-1]), r = bias(rp[1]);
-        const uint32_t u1 = bias(rp[-FROWW]), d1 = bias(rp[FROWW]);
-        uint32_t sumA = c + u1 + d1 + sh_l1(l, c) + sh_r1(c, r);
-        uint32_t flags;
-        if constexpr (M == 1) {
-          // 5 values in [1,31]: sum <= 155; sum > 80 <=> bit 7 of (sum + 47)
-          flags = ((sumA + 0x2F2F2F2Fu) >> 7) & 0x01010101u;
-        } else {
-          const uint32_t ul = bias(rp[-FROWW - 1]), ur = bias(rp[-FROWW + 1]);
-          const uint32_t dl = bias(rp[FROWW - 1]), dr = bias(rp[FROWW + 1]);
-          const uint32_t sumB = bias(rp[-2 * FROWW]) + bias(rp[2 * FROWW]) + sh_2(l, c) + sh_2(c, r) +
-                                sh_l1(ul, u1) + sh_r1(u1, ur) + sh_l1(dl, d1);
-          sumA += sh_r1(d1, dr);  // 6 values <= 186; sumB: 7 values <= 217
-          // 16-bit lanes: total > 16*13 = 208
-          const uint32_t lo = (sumA & 0x00FF00FFu) + (sumB & 0x00FF00FFu);
-          const uint32_t hi = ((sumA >> 8) & 0x00FF00FFu) + ((sumB >> 8) & 0x00FF00FFu);
-          const uint32_t flo = ((lo + (0x8000u - 209u) * 0x00010001u) >> 15) & 0x00010001u;
-          const uint32_t fhi = ((hi + (0x8000u - 209u) * 0x00010001u) >> 15) & 0x00010001u;
-          flags = flo | (fhi << 8);
-        }
-        wSt[row * FROWW + w] = flags;
-      }
-    }
     // ---- phase A4: integer statistics of iteration j straight from the staged words
     if (upd) {
       // defectors per 5-site group (spgg.py:586-592), bit-sliced: one thread = 32 sites
@@ -407,7 +375,35 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       const int wo = rr * FROWW + (CPAD / 4) + lane;      // word of (rr, 4*lane) in a tile-row-indexed plane
       const uint32_t RW = st_R[wo + M * FROWW];
       const uint32_t CW = wC[wo + 2 * FROWW];
-      const uint32_t StW = ACTION ? CW : wSt[wo];          // post-action state flags, 4 sites
+      // post-action state of the 4 sites (= pre-action state of the next iteration, spgg.py:409/423)
+      uint32_t StW;
+      if constexpr (ACTION) {
+        StW = CW;                                          // own previous action (spgg.py:291)
+      } else {
+        // reputation state (spgg.py:292-307): v = R + 16 in each byte (|R| <= 15 is a launch
+        // precondition); sum of n values v > 16 n  <=>  sum of R > 0
+        const uint32_t *rp = st_R + wo + M * FROWW;
+        auto bias = [](uint32_t x) { return (x ^ 0x10101010u) & 0x1F1F1F1Fu; };
+        const uint32_t c = bias(RW), l = bias(rp[-1]), r = bias(rp[1]);
+        const uint32_t u1 = bias(rp[-FROWW]), d1 = bias(rp[FROWW]);
+        uint32_t sumA = c + u1 + d1 + sh_l1(l, c) + sh_r1(c, r);
+        if constexpr (M == 1) {
+          // 5 values in [1,31]: sum <= 155; sum > 80 <=> bit 7 of (sum + 47)
+          StW = ((sumA + 0x2F2F2F2Fu) >> 7) & 0x01010101u;
+        } else {
+          const uint32_t ul = bias(rp[-FROWW - 1]), ur = bias(rp[-FROWW + 1]);
+          const uint32_t dl = bias(rp[FROWW - 1]), dr = bias(rp[FROWW + 1]);
+          const uint32_t sumB = bias(rp[-2 * FROWW]) + bias(rp[2 * FROWW]) + sh_2(l, c) + sh_2(c, r) +
+                                sh_l1(ul, u1) + sh_r1(u1, ur) + sh_l1(dl, d1);
+          sumA += sh_r1(d1, dr);  // 6 values <= 186; sumB: 7 values <= 217
+          // 16-bit lanes: total > 16*13 = 208
+          const uint32_t lo = (sumA & 0x00FF00FFu) + (sumB & 0x00FF00FFu);
+          const uint32_t hi = ((sumA >> 8) & 0x00FF00FFu) + ((sumB >> 8) & 0x00FF00FFu);
+          const uint32_t flo = ((lo + (0x8000u - 209u) * 0x00010001u) >> 15) & 0x00010001u;
+          const uint32_t fhi = ((hi + (0x8000u - 209u) * 0x00010001u) >> 15) & 0x00010001u;
+          StW = flo | (fhi << 8);
+        }
+      }
       sum_r = __dp4a((int)RW, 0x01010101, sum_r);          // spgg.py:394
       uint32_t codeW = 0;
       float vc[4], vu[4], vd[4], vl[2], vr[2], vu2[4], vd2[4], vul = 0.f, vur = 0.f, vdl = 0.f, vdr = 0.f;
@@ -454,16 +450,17 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       uint32_t coopW = 0, rnewW = 0;
       float qfin[4];
       int eidx[4];
+      const uint32_t rowoffW = StW << 3;  // byte offset of row s' inside a site's 16 bytes, 4 sites
       if (upd) {
         float qe[4], na[4], nb_[4];
+        // byte offset of Q[s][a] (a = !coop) inside a site's 16 bytes: 4 * (2 s + a), 4 sites at once
+        const uint32_t eoffW = ((codeW & 0x01010101u) << 3) | ((((codeW >> 1) & 0x01010101u) ^ 0x01010101u) << 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float *qs = reinterpret_cast<const float *>(qbuf + qoff[k]);
-          const uint32_t code = (codeW >> (8 * k)) & 0xFFu;
-          const int s_new = (StW >> (8 * k)) & 1u;
-          eidx[k] = (int)(((code & 1u) << 1) | (((code >> 1) & 1u) ^ 1u));  // index of Q[s][a], a = !coop
-          qe[k] = qs[eidx[k]];
-          const float2 nrow = *reinterpret_cast<const float2 *>(qs + 2 * s_new);  // pre-update row of s'
+          const unsigned char *qs = qbuf + qoff[k];
+          eidx[k] = (int)__byte_perm(eoffW, 0, 0x4440 + k);
+          qe[k] = *reinterpret_cast<const float *>(qs + eidx[k]);
+          const float2 nrow = *reinterpret_cast<const float2 *>(qs + __byte_perm(rowoffW, 0, 0x4440 + k));  // pre-update row of s'
           na[k] = nrow.x; nb_[k] = nrow.y;
         }
 #pragma unroll
@@ -515,7 +512,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           if (best > 0.f) pk_best += second ? 0x10001u : 1u;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) reinterpret_cast<float *>(qbuf + qoff[k])[eidx[k]] = qfin[k];
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<float *>(qbuf + qoff[k] + eidx[k]) = qfin[k];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 qn = *reinterpret_cast<const float4 *>(qbuf + qoff[k]);   // after both updates
@@ -527,9 +524,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       if (sel) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int s_new = (StW >> (8 * k)) & 1u;
           const float2 grow = *reinterpret_cast<const float2 *>(
-              reinterpret_cast<const float *>(qbuf + qoff[k]) + 2 * s_new);      // Q[s'] after the update
+              qbuf + qoff[k] + __byte_perm(rowoffW, 0, 0x4440 + k));             // Q[s'] after the update
           const bool explore = (w4[k] >> 8) < thr;
           const int rnd = (int)(w4[k] & 1u);
           const int greedy = (grow.y > grow.x) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
