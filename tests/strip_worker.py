@@ -91,6 +91,30 @@ def gpu_strips(rank, world, precision, second, state, L, n_steps):
     dist.barrier()
 
 
+def gpu_sweep(rank, world):
+    """Replica sweep sharded over ranks == the same replicas run one by one."""
+    import torch
+    import spgg_b200
+    from spgg_b200 import sweep
+    from helpers import C1, C2, full_params
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+    plist = [full_params(dict(C1, L=64, r=r, influence_factor=k)) for r in (3.0, 4.0) for k in (0.0, 1.0)]
+    plist += [full_params(dict(C2, L=64, r=r)) for r in (3.6, 5.0)]
+    plist += [full_params(dict(C1, L=128, r=3.0))]
+    seeds = [100 + i for i in range(len(plist))]
+    res = sweep.run_sweep(plist, seeds, iterations=25, max_batch=3, chunk=10)
+    assert len(res) == len(plist)
+    if rank == 0:
+        for p, sd, o in zip(plist, seeds, res):
+            single = sweep.run_batch([p], [sd], 25, chunk=25, device=torch.cuda.current_device())[0]
+            assert o["iterations"] == single["iterations"] == 25
+            assert np.array_equal(o["S"], single["S"]) and np.array_equal(o["R"], single["R"])
+            for k in ("coop_rate_history", "switch_C_to_D", "group_comp_d2_history"):
+                assert np.array_equal(o["series"][k], single["series"][k]), k
+            np.testing.assert_allclose(o["series"]["avg_q_s0_c_history"],
+                                       single["series"]["avg_q_s0_c_history"], rtol=1e-6, atol=1e-9)
+
+
 def main():
     import torch.distributed as dist
     mode = sys.argv[1]
@@ -100,6 +124,8 @@ def main():
     try:
         if mode == "host":
             host_logic(rank, world)
+        elif mode == "sweep":
+            gpu_sweep(rank, world)
         else:
             precision, second, state, L, n = sys.argv[3:8]
             gpu_strips(rank, world, precision, second == "1", state, int(L), int(n))

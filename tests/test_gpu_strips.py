@@ -38,3 +38,12 @@ def test_strips_equal_single_lattice_nccl(precision, second, state, L):
     res = launch_ranks(["gpu", "nccl", precision, second, state, L, 12], world, timeout=600)
     for rc, out in res:
         assert rc == 0, out
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_replica_sweep_sharded_over_ranks(world):
+    """BASELINE config 3: the r x kappa grid as batched replicas dealt to the ranks; each replica
+    must equal its stand-alone run bit for bit (S, R, integer series)."""
+    res = launch_ranks(["sweep", "gloo"], world, timeout=600)
+    for rc, out in res:
+        assert rc == 0, out

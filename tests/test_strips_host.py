@@ -34,3 +34,21 @@ def test_halo_exchange_and_stat_reduction_over_gloo(world):
     res = launch_ranks(["host", "gloo"], world, timeout=180)
     for rc, out in res:
         assert rc == 0, out
+
+
+def test_sweep_plan_groups_and_deals_round_robin():
+    from spgg_b200 import sweep
+    plist = ([dict(L=200, use_second_order=False, r=r) for r in range(10)] +
+             [dict(L=200, use_second_order=True, r=r) for r in range(6)] +
+             [dict(L=100, state_representation="action")])
+    for world in (1, 2, 8):
+        pl = sweep.plan(plist, world, max_batch=4)
+        seen = sorted(i for _r, b in pl for i in b)
+        assert seen == list(range(len(plist)))                    # every replica exactly once
+        for _r, b in pl:
+            assert len(b) <= 4
+            assert len({sweep.group_key(plist[i]) for i in b}) == 1   # a batch shares its geometry
+        assert {r for r, _b in pl} <= set(range(world))
+        if world == 8:
+            assert len({r for r, _b in pl}) >= 6                   # the work is spread over the GPUs
+    assert sweep.plan(plist, 2, 4) == sweep.plan(plist, 2, 4)      # deterministic
