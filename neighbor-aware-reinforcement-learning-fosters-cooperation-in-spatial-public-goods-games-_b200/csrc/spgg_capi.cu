@@ -336,7 +336,8 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     bool ok = (h->mode == MODE_F32_I8) && (g.L % TC == 0) && (g.rows % FTR == 0) &&
               getenv("SPGG_NO_FAST") == nullptr;
     for (int r = 0; r < n_replicas && ok; ++r)
-      ok = h->rc_host[r].rmin_i >= -15 && h->rc_host[r].rmax_i <= 15;
+      ok = h->rc_host[r].rmin_i >= -15 && h->rc_host[r].rmax_i <= 15 && h->rc_host[r].gain_i >= 0 &&
+           h->rc_host[r].loss_i >= 0;
     (void)r0;
     h->fast = ok;
   }

@@ -213,7 +213,12 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   }
   const uint32_t thr = sel ? a.thr_tab[(long long)(a.rel + 1) * g.n_rep + rep] : 0u;
   const float alpha = rc.alpha_f, gamma = rc.gamma_f, kappa = rc.kappa_f;
-  const int gain_i = rc.gain_i, loss_i = rc.loss_i, rmin_i = rc.rmin_i, rmax_i = rc.rmax_i;
+  // byte-parallel reputation update: steps beyond the width of [R_min, R_max] saturate alike
+  // (gain and loss are non-negative on this path, spgg_create checks)
+  const int g31 = min(rc.gain_i, 31), l31 = min(rc.loss_i, 31);
+  const uint32_t r_dsum = (uint32_t)(g31 + l31);
+  const uint32_t r_k = (uint32_t)(32 - l31) * 0x01010101u;
+  const uint32_t r_lo = (uint32_t)(rc.rmin_i + 48) * 0x01010101u, r_hi = (uint32_t)(rc.rmax_i + 48) * 0x01010101u;
   const bool has_ratio = rc.has_ratio != 0;
 
   // per-thread statistics: exact 32-bit integer counters + fp32 partial sums.
@@ -530,12 +535,16 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           const int rnd = (int)(w4[k] & 1u);
           const int greedy = (grow.y > grow.x) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
           const int a_new = explore ? rnd : greedy;      // algorithms.py:109
-          const int r_old = (int)(int8_t)(RW >> (8 * k));
-          int t = r_old + (a_new == 0 ? gain_i : -loss_i);  // spgg.py:321-323
-          t = min(max(t, rmin_i), rmax_i);
           coopW |= (uint32_t)(a_new ^ 1) << (8 * k);
-          rnewW |= ((uint32_t)t & 0xFFu) << (8 * k);
         }
+        // reputation update (spgg.py:321-323) for the 4 sites at once, bytes biased so that no
+        // carry crosses a byte: x = R + 48 = (R + 16) + 32 + (coop ? gain : -loss), clamped
+        uint32_t x = ((RW ^ 0x10101010u) & 0x1F1F1F1Fu) + coopW * r_dsum + r_k;   // in [2, 94]
+        uint32_t m = ((((x | 0x80808080u) - r_lo) >> 7) & 0x01010101u) * 0xFFu;  // x >= lo
+        x = (x & m) | (r_lo & ~m);
+        m = ((((r_hi | 0x80808080u) - x) >> 7) & 0x01010101u) * 0xFFu;           // hi >= x
+        x = (x & m) | (r_hi & ~m);
+        rnewW = (x + 0x50505050u) ^ 0x80808080u;                                 // back to int8 bytes: x - 48
       }
       if (sel) {
         // reward code of iteration j+1: SigmaN<<3 | C_j<<2 | coop<<1 | state, 4 sites per word
