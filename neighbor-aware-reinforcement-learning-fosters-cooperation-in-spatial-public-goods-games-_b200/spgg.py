@@ -120,6 +120,9 @@ class SPGG:
 
     def run(self, filename):
         """spgg.py:325-637."""
+        return run_models([self], [filename])[0]
+
+    def _check_runnable(self):
         if getattr(self, "_bad_state", None) is not None:
             raise ValueError(f"Unknown state_representation: {self._bad_state}. "
                              f"Must be 'reputation' or 'action'")
@@ -127,83 +130,10 @@ class SPGG:
             raise ValueError(
                 f"algorithm '{getattr(self.algorithm, 'name', type(self.algorithm).__name__)}' is not "
                 "built into the fused CUDA step (only Q-learning is); there is no CPU fallback")
-        L = self.L
-        N = L * L
-        precision = self.params.get("precision", "fp32")
-        draws = self.params.get("draws", "philox")
-        chunk_max = int(self.params.get("chunk", 4096))
-        if draws == "numpy":
-            chunk_max = max(1, min(chunk_max, (64 << 20) // (9 * N) or 1))
-        pdict = self._engine_params()
-        eps0 = float(self.algorithm.epsilon)
 
-        snapshots_dir = os.path.join(self.folder, 'plots', 'snapshots') if self.folder else 'snapshots'
-        os.makedirs(snapshots_dir, exist_ok=True)                      # spgg.py:365-366
-
-        eng = Engine(pdict, seeds=self._philox_seed, precision=precision,
-                     device=int(self.params.get("device", 0)))
-        try:
-            eng.set_state(self._Sn, self.R, self.q_table)
-            rows_it, sum_r_before = [], []
-            done, stopped = 0, False
-            snaps = {}
-            T = int(self.iterations)
-            cut_points = sorted(i - 1 for i in self.snapshot_iters if 1 <= i <= T)
-            with h5lite.open_file(filename, "w") as data_file:
-                while done < T and not stopped:
-                    if done in cut_points or (done == 0 and 1 in self.snapshot_iters):
-                        self._snapshot(eng, done + 1, data_file, snaps)
-                    nxt = min([c for c in cut_points if c > done] + [T])
-                    n = min(nxt - done, chunk_max)
-                    if draws == "numpy":
-                        u = np.empty((n, L, L))
-                        b = np.empty((n, L, L), np.uint8)
-                        for t in range(n):                              # algorithms.py:105,108
-                            u[t] = self._rng.rand(L, L)
-                            b[t] = self._rng.randint(0, 2, size=(L, L))
-                        eng.set_replay(u, b)
-                    eng.step(n)
-                    st = eng.status()
-                    rows = eng.stats()
-                    k = int(st.iteration) - done                        # iterations really completed
-                    rows_it.append(rows[1:k + 1])
-                    sum_r_before.append(rows[:k, L_.ST_SUM_R])
-                    stop_sum_r = rows[k, L_.ST_SUM_R]
-                    done += k
-                    if st.stopped_at >= 0 and st.stopped_at <= done:
-                        stopped = True
-                        if (done + 1) in self.snapshot_iters and (done + 1) not in snaps:
-                            self._snapshot(eng, done + 1, data_file, snaps)   # spgg.py:397 precedes :405
-                S, R, Q = eng.get_state()
-                rows_it = np.vstack(rows_it) if rows_it else np.zeros((0, L_.NSTAT))
-                sum_r_before = np.concatenate(sum_r_before) if sum_r_before else np.zeros(0)
-                ser = series.assemble(rows_it, sum_r_before, N, self.params, eps0, stopped=stopped,
-                                      stop_sum_r=stop_sum_r if stopped else 0.0,
-                                      stop_all_coop=bool((S == 0).all()))
-                self._write_final(data_file, ser, S, R)
-            self.kernel_launches = int(eng.status().kernel_launches)
-        finally:
-            eng.close()
-
-        # post-run attributes the reference leaves behind
-        self.q_table, self.R, self._Sn = Q, R, S.astype(np.int64)
-        self._S = [(self._Sn == j).astype(int) for j in range(self.num_of_strategies)]
-        for _ in range(done):
-            self.algorithm.decay_epsilon()
-        self.epsilon = self.algorithm.epsilon
-        self.avg_q_history = {k: list(ser[f"avg_{k}_history"]) for k in series.Q_NAMES}
-        self.q_history_by_strategy = {
-            g: {k: list(ser[f"{g}_{k}_history"]) for k in series.Q_NAMES}
-            for g in ("cooperators", "defectors")}
-        self.group_composition_history = [list(ser[f"group_comp_d{k}_history"]) for k in range(6)]
-        it = ser["it_records_final"]
-        mean_P = float(it[-1, 3]) if len(it) else float("nan")
-        nC = int((S == 0).sum())
-        return (nC / N, (N - nC) / N, mean_P)
-
-    def _snapshot(self, eng, i, data_file, snaps):
+    def _snapshot(self, eng, i, data_file, snaps, replica=0):
         """State before iteration i acts (spgg.py:397-402)."""
-        S, R, _ = eng.get_state(want_q=False)
+        S, R, _ = eng.get_state(replica, want_q=False)
         data_file.create_dataset(f"R_snapshot_{i}", data=R)
         rep_hist, rep_bins = np.histogram(R, bins=20, range=(self.R_min, self.R_max))
         data_file.create_dataset(f"rep_hist_{i}", data=rep_hist)
@@ -239,3 +169,108 @@ class SPGG:
         clusters, n_clusters = label(S == 0)
         sizes = np.bincount(clusters.ravel(), minlength=n_clusters + 1)[1:]
         data_file.create_dataset("cluster_sizes", data=sizes.astype(np.int64))
+
+
+def run_models(models, filenames):
+    """``SPGG.run`` for one or several models at once (spgg.py:325-637 for each).  Models that
+    share the lattice geometry (L, use_second_order, state_representation, precision) run as
+    batched replicas of ONE device handle - the GPU counterpart of the reference's one process
+    per parameter tuple (runner.py:117-156).  Returns the list of ``run`` return values."""
+    models = list(models)
+    for m in models:
+        m._check_runnable()
+    m0 = models[0]
+    L, N, n = m0.L, m0.L * m0.L, len(models)
+    precision = m0.params.get("precision", "fp32")
+    draws = m0.params.get("draws", "philox")
+    chunk_max = int(m0.params.get("chunk", 4096))
+    for m in models[1:]:
+        if (m.L, bool(m.use_second_order), m.state_representation, m.params.get("precision", "fp32"),
+                int(m.iterations)) != (L, bool(m0.use_second_order), m0.state_representation, precision,
+                                       int(m0.iterations)):
+            raise ValueError("batched models must share L, use_second_order, state_representation, "
+                             "precision and iterations")
+    if draws == "numpy":
+        if n != 1:
+            raise ValueError("draws='numpy' (replay of the reference's stream) runs one model at a time")
+        chunk_max = max(1, min(chunk_max, (64 << 20) // (9 * N) or 1))
+    eps0 = [float(m.algorithm.epsilon) for m in models]
+    for m in models:
+        snapshots_dir = os.path.join(m.folder, 'plots', 'snapshots') if m.folder else 'snapshots'
+        os.makedirs(snapshots_dir, exist_ok=True)                      # spgg.py:365-366
+    T = int(m0.iterations)
+    cut_points = sorted(i - 1 for i in m0.snapshot_iters if 1 <= i <= T)
+    eng = Engine([m._engine_params() for m in models], seeds=[m._philox_seed for m in models],
+                 precision=precision, device=int(m0.params.get("device", 0)))
+    files = [h5lite.open_file(f, "w") for f in filenames]
+    results = []
+    try:
+        for r, m in enumerate(models):
+            eng.set_state(m._Sn, m.R, m.q_table, replica=r)
+        rows_it = [[] for _ in models]
+        sum_r_before = [[] for _ in models]
+        stop_sum_r = [0.0] * n
+        done = [0] * n
+        stopped = [False] * n
+        snaps = [{} for _ in models]
+        t = 0                                       # iterations launched so far (running replicas are in lockstep)
+        while t < T and not all(stopped):
+            if t in cut_points or (t == 0 and 1 in m0.snapshot_iters):
+                for r, m in enumerate(models):
+                    if not stopped[r]:
+                        m._snapshot(eng, t + 1, files[r], snaps[r], r)
+            nxt = min([c for c in cut_points if c > t] + [T])
+            k_req = min(nxt - t, chunk_max)
+            if draws == "numpy":
+                u = np.empty((k_req, L, L))
+                b = np.empty((k_req, L, L), np.uint8)
+                for i in range(k_req):                                  # algorithms.py:105,108
+                    u[i] = m0._rng.rand(L, L)
+                    b[i] = m0._rng.randint(0, 2, size=(L, L))
+                eng.set_replay(u, b)
+            eng.step(k_req)
+            for r, m in enumerate(models):
+                if stopped[r]:
+                    continue
+                st = eng.status(r)
+                rows = eng.stats(r)
+                k = int(st.iteration) - done[r]                         # iterations really completed
+                rows_it[r].append(rows[1:k + 1])
+                sum_r_before[r].append(rows[:k, L_.ST_SUM_R])
+                stop_sum_r[r] = rows[k, L_.ST_SUM_R]
+                done[r] += k
+                if st.stopped_at >= 0 and st.stopped_at <= done[r]:
+                    stopped[r] = True
+                    if (done[r] + 1) in m.snapshot_iters and (done[r] + 1) not in snaps[r]:
+                        m._snapshot(eng, done[r] + 1, files[r], snaps[r], r)   # spgg.py:397 precedes :405
+            t += k_req
+        launches = int(eng.status().kernel_launches)
+        for r, m in enumerate(models):
+            S, R, Q = eng.get_state(r)
+            ri = np.vstack(rows_it[r]) if rows_it[r] else np.zeros((0, L_.NSTAT))
+            sb = np.concatenate(sum_r_before[r]) if sum_r_before[r] else np.zeros(0)
+            ser = series.assemble(ri, sb, N, m.params, eps0[r], stopped=stopped[r],
+                                  stop_sum_r=stop_sum_r[r] if stopped[r] else 0.0,
+                                  stop_all_coop=bool((S == 0).all()))
+            m._write_final(files[r], ser, S, R)
+            m.kernel_launches = launches
+            # post-run attributes the reference leaves behind
+            m.q_table, m.R, m._Sn = Q, R, S.astype(np.int64)
+            m._S = [(m._Sn == j).astype(int) for j in range(m.num_of_strategies)]
+            for _ in range(done[r]):
+                m.algorithm.decay_epsilon()
+            m.epsilon = m.algorithm.epsilon
+            m.avg_q_history = {k: list(ser[f"avg_{k}_history"]) for k in series.Q_NAMES}
+            m.q_history_by_strategy = {
+                g: {k: list(ser[f"{g}_{k}_history"]) for k in series.Q_NAMES}
+                for g in ("cooperators", "defectors")}
+            m.group_composition_history = [list(ser[f"group_comp_d{k}_history"]) for k in range(6)]
+            it = ser["it_records_final"]
+            mean_P = float(it[-1, 3]) if len(it) else float("nan")
+            nC = int((S == 0).sum())
+            results.append((nC / N, (N - nC) / N, mean_P))
+    finally:
+        for f in files:
+            f.close()
+        eng.close()
+    return results

@@ -114,3 +114,29 @@ def test_other_td_rules_fail_loudly(tmp_path):
         m = spgg_b200.SPGG(L=16, iterations=3, algorithm=algo, seed=1)
         with pytest.raises(ValueError, match="no CPU fallback"):
             m.run(str(tmp_path / "x.h5"))
+
+
+def test_gpu_runner_batches_equal_single_experiments(tmp_path):
+    """run_experiments (batched replicas) == run_one_experiment per tuple; folder layout and
+    file names of runner.py:74-85,104."""
+    from spgg_b200 import runner
+    combos = [(3.0, 1.0, False, 0.8, 0.95, 1.0, "reputation", "qlearning"),
+              (4.0, 0.5, False, 0.8, 0.95, 1.0, "reputation"),
+              (4.0, 1.0, True, 0.8, 1.0, 1.0, "action", "qlearning"),
+              (3.6, 0.0, False, 0.8, 1.0, 0.5)]
+    kw = dict(L=64, iterations=120, seed=5)
+    res = runner.run_experiments(combos, num_processes=2, use_progress_bar=False,
+                                 base_dir=str(tmp_path / "batch"), **kw)
+    assert [p for p, _ in res] == combos
+    for (p, (coop, rep_mean)) in res:
+        single_p, (coop1, rep1) = runner.run_one_experiment(p, base_dir=str(tmp_path / "single"), **kw)
+        assert coop == coop1 and rep_mean == rep1 == 0
+        folder = runner.get_folder_name(*runner._unpack(p))
+        a = _read(str(tmp_path / "batch" / folder / "data" / "experiment_data.h5"))
+        b = _read(str(tmp_path / "single" / folder / "data" / "experiment_data.h5"))
+        assert sorted(a) == sorted(b)
+        for k in ("Sn_final", "R_final", "coop_rate_history", "switch_C_to_D", "Sn_snapshot_100",
+                  "R_snapshot_10", "rep_hist_final", "cluster_sizes"):
+            assert np.array_equal(a[k], b[k]), k
+        for sub in ("configurations", "reputations", os.path.join("plots", "snapshots"), "data"):
+            assert os.path.isdir(tmp_path / "batch" / folder / sub)

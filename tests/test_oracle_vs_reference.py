@@ -94,3 +94,13 @@ def test_dropin_class_has_the_reference_signature_and_exports():
         if k in ("S_in_one",):
             continue
         assert k in b.params, k
+
+
+def test_runner_folder_name_equals_reference():
+    import importlib
+    from spgg_b200 import runner
+    ref_harness.import_reference()
+    ref_runner = importlib.import_module("src.experiments.runner")
+    for args in [(3.0, 1.0, False, 0.8, 0.95, 1.0), (3.6, 0.0, True, 0.1, 1.0, 0.5, "action"),
+                 (5, 2, True, 0.8, 0.9, 0.25, "reputation", "double_qlearning")]:
+        assert runner.get_folder_name(*args) == ref_runner.get_folder_name(*args)

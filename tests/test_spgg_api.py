@@ -114,3 +114,18 @@ def test_assemble_early_exit_lengths():
     assert ser["rep_avg_history_final"][-1] == 1.0
     assert ser["epsilon_history_final"].shape == (T,)
     assert ser["switch_C_to_D"].dtype == np.int64
+
+
+def test_runner_folder_names_and_tuple_formats():
+    """src/experiments/runner.py:11-45, 62-72."""
+    from spgg_b200 import runner
+    assert runner.get_folder_name(3.0, 1.0, False, 0.8, 0.95, 1.0) == \
+        "results_r3.0_inf1.0_orderFalse_alpha0.8_rw0.95_rgC1.00"
+    assert runner.get_folder_name(4.0, 0.5, True, 0.8, 1.0, 0.5, "action", "sarsa") == \
+        "results_r4.0_inf0.5_orderTrue_alpha0.8_rw1.00_rgC0.50_action_sarsa"
+    assert runner._unpack((3.0, 1.0, False, 0.8, 0.95, 1.0)) == \
+        (3.0, 1.0, False, 0.8, 0.95, 1.0, "reputation", "qlearning")
+    assert runner._unpack((3.0, 1.0, False, 0.8, 0.95, 1.0, "action"))[-2:] == ("action", "qlearning")
+    with pytest.raises(ValueError):
+        runner._unpack((1, 2, 3))
+    assert runner.RUNNER_MODEL["L"] == 100 and runner.RUNNER_MODEL["iterations"] == 100001
