@@ -41,6 +41,8 @@ extern "C" {
 
 /* algorithm (algorithms.py:344-383) */
 #define SPGG_ALGO_QLEARNING 0
+#define SPGG_ALGO_SARSA 1          /* algorithms.py:136-178, applied as spgg.py:431-438,450-454 */
+#define SPGG_ALGO_EXPECTED_SARSA 2 /* algorithms.py:181-234, spgg.py:455-463 */
 
 /* reputation storage in fp32 mode */
 #define SPGG_RSTORE_AUTO 0 /* int8 when rep_gain_C, delta_R_D, R_min, R_max are multiples of 2^-k that fit */
@@ -129,6 +131,11 @@ int spgg_init_random(spgg_t *h, int replica, uint64_t seed);
  * `randint(0,2,(L,L))`), each n_steps*rows*L.  Single replica only.  Consumed
  * by the following spgg_step calls; Philox is used once they run out. */
 int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const uint8_t *b);
+/* Same with n_pairs (rand, randint) pairs per iteration, arrays laid out
+ * (n_steps, n_pairs, rows, L): SARSA consumes three pairs per iteration - the action
+ * (algorithms.py:145-148 via spgg.py:410), the next action of the update (spgg.py:433) and
+ * the next action of the NI statistic (spgg.py:452); every other rule consumes one. */
+int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const double *u, const uint8_t *b);
 
 /* Run n_steps iterations of the loop body spgg.py:368-592 for all replicas
  * (asynchronous on `cuda_stream`, a cudaStream_t or NULL). */

@@ -25,7 +25,7 @@ ST_SUM_NI, ST_N_BEST_POS, ST_N_BEST_2ND, ST_GMAX = 30, 31, 32, 33
 
 PREC_FP32, PREC_FP64 = 0, 1
 STATE_REPUTATION, STATE_ACTION = 0, 1
-ALGO_QLEARNING = 0
+ALGO_QLEARNING, ALGO_SARSA, ALGO_EXPECTED_SARSA = 0, 1, 2
 RSTORE_AUTO, RSTORE_INT8, RSTORE_FP32 = 0, 1, 2
 E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4
 
@@ -53,6 +53,7 @@ class Status(C.Structure):
 
 EXPORTS = (
     "spgg_create", "spgg_destroy", "spgg_set_state", "spgg_get_state", "spgg_set_replay",
+    "spgg_set_replay_pairs",
     "spgg_step", "spgg_sync", "spgg_get_stats", "spgg_query", "spgg_halo_bytes",
     "spgg_halo_pack", "spgg_halo_unpack", "spgg_phase_kernel", "spgg_phase_gmax",
     "spgg_gmax_device_ptr", "spgg_begin_steps", "spgg_end_steps", "spgg_last_error",
@@ -79,6 +80,7 @@ def load():
     lib.spgg_set_state.argtypes = [vp, i32, vp, vp, vp]
     lib.spgg_get_state.argtypes = [vp, i32, vp, vp, vp]
     lib.spgg_set_replay.argtypes = [vp, i32, vp, vp]
+    lib.spgg_set_replay_pairs.argtypes = [vp, i32, i32, vp, vp]
     lib.spgg_step.argtypes = [vp, i32, vp]
     lib.spgg_sync.argtypes = [vp]
     lib.spgg_get_stats.argtypes = [vp, i32, i32, i32, vp]

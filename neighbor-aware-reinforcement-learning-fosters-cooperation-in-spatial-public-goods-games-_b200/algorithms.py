@@ -48,13 +48,15 @@ class QLearning(RLAlgorithm):
 
 
 class SARSA(RLAlgorithm):
-    """On-policy TD target (algorithms.py:152-178); not yet compiled into the fused step."""
+    """TD target Q(s',a') with a' drawn from the epsilon-greedy policy (algorithms.py:152-178;
+    three draw pairs per iteration, spgg.py:410,433,452)."""
+    kernel_tag = "sarsa"
     name = "sarsa"
 
 
 class ExpectedSARSA(RLAlgorithm):
-    """Expected TD target under the epsilon-greedy policy (algorithms.py:197-234);
-    not yet compiled into the fused step."""
+    """Expected TD target under the epsilon-greedy policy (algorithms.py:197-234)."""
+    kernel_tag = "expected_sarsa"
     name = "expected_sarsa"
 
 

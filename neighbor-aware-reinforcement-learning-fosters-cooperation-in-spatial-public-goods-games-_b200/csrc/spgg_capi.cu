@@ -78,6 +78,7 @@ struct spgg_handle {
   FastMaps fmaps[2];  // [cur]: loads from plane set cur, stores into cur^1
   std::vector<double> eps_host;
   std::vector<uint32_t> thr_host;
+  int replay_pairs = 1;
   long long replay_first = 0, replay_n = 0;  // draws cover iterations replay_first+1 .. replay_first+replay_n
   // host bookkeeping
   long long iter = 0;
@@ -291,7 +292,8 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     return fail(SPGG_E_INVALID, "Unknown state_representation code %d", p0.state_mode);
   if (p0.precision != SPGG_PREC_FP32 && p0.precision != SPGG_PREC_FP64)
     return fail(SPGG_E_INVALID, "unknown precision %d", p0.precision);
-  if (p0.algorithm != SPGG_ALGO_QLEARNING)
+  if (p0.algorithm != SPGG_ALGO_QLEARNING && p0.algorithm != SPGG_ALGO_SARSA &&
+      p0.algorithm != SPGG_ALGO_EXPECTED_SARSA)
     return fail(SPGG_E_UNSUPPORTED, "algorithm code %d is not built into the fused kernel", p0.algorithm);
   if (p0.row0 < 0 || p0.row0 + p0.rows > p0.L) return fail(SPGG_E_INVALID, "row0/rows outside the lattice");
   for (int r = 1; r < n_replicas; ++r) {
@@ -334,7 +336,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   {
     const RepConst &r0 = h->rc_host[0];
     bool ok = (h->mode == MODE_F32_I8) && (g.L % TC == 0) && (g.rows % FTR == 0) &&
-              getenv("SPGG_NO_FAST") == nullptr;
+              p0.algorithm == SPGG_ALGO_QLEARNING && getenv("SPGG_NO_FAST") == nullptr;
     for (int r = 0; r < n_replicas && ok; ++r)
       ok = h->rc_host[r].rmin_i >= -15 && h->rc_host[r].rmax_i <= 15 && h->rc_host[r].gain_i >= 0 &&
            h->rc_host[r].loss_i >= 0;
@@ -575,7 +577,14 @@ extern "C" int spgg_get_state(spgg_t *h, int rep, uint8_t *S, double *R, double 
 }
 
 extern "C" int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const uint8_t *b) {
+  return spgg_set_replay_pairs(h, n_steps, 1, u, b);
+}
+
+extern "C" int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const double *u, const uint8_t *b) {
   if (!h) return fail(SPGG_E_INVALID, "null handle");
+  if (n_steps > 0 && n_pairs != (h->params[0].algorithm == SPGG_ALGO_SARSA ? 3 : 1))
+    return fail(SPGG_E_INVALID, "this TD rule consumes %d draw pair(s) per iteration, got %d",
+                h->params[0].algorithm == SPGG_ALGO_SARSA ? 3 : 1, n_pairs);
   if (h->n_rep != 1) return fail(SPGG_E_UNSUPPORTED, "replay draws are supported for a single replica");
   int rcode = finish_pending(h);
   if (rcode) return rcode;
@@ -584,7 +593,8 @@ extern "C" int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const ui
   h->d_u = nullptr; h->d_b = nullptr; h->replay_n = 0;
   if (n_steps <= 0) return SPGG_OK;
   if (!u || !b) return fail(SPGG_E_INVALID, "spgg_set_replay: null draw arrays");
-  const size_t n = (size_t)n_steps * h->g.site_stride;
+  const size_t n = (size_t)n_steps * n_pairs * h->g.site_stride;
+  h->replay_pairs = n_pairs;
   CUDA_TRY(cudaMalloc((void **)&h->d_u, n * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&h->d_b, n));
   CUDA_TRY(cudaMemcpy(h->d_u, u, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -668,8 +678,17 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   a.gmax = h->d_gmax; a.stats = h->d_stats; a.partials = h->d_partials;
   a.tickets = h->d_tickets; a.stop_at = h->d_stop;
   a.eps_tab = h->d_eps; a.thr_tab = h->d_thr;
-  a.u = replay ? h->d_u + (size_t)draw * h->g.site_stride : nullptr;
-  a.b = replay ? h->d_b + (size_t)draw * h->g.site_stride : nullptr;
+  const size_t np_ = (size_t)h->replay_pairs, ss = (size_t)h->g.site_stride;
+  a.u = replay ? h->d_u + (size_t)draw * np_ * ss : nullptr;
+  a.b = replay ? h->d_b + (size_t)draw * np_ * ss : nullptr;
+  a.algo = h->params[0].algorithm;
+  // SARSA: pairs 1 and 2 of iteration j (entry j-1-replay_first) feed the update launched now
+  const long long ue = j - 1 - h->replay_first;
+  const bool upd_replay = do_update && a.algo == SPGG_ALGO_SARSA && h->d_u && np_ == 3 && ue >= 0 && ue < h->replay_n;
+  a.u2 = upd_replay ? h->d_u + ((size_t)ue * 3 + 1) * ss : nullptr;
+  a.b2 = upd_replay ? h->d_b + ((size_t)ue * 3 + 1) * ss : nullptr;
+  a.u3 = upd_replay ? h->d_u + ((size_t)ue * 3 + 2) * ss : nullptr;
+  a.b3 = upd_replay ? h->d_b + ((size_t)ue * 3 + 2) * ss : nullptr;
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
 #ifdef SPGG_TRACE

@@ -97,6 +97,10 @@ struct KArgs {
   const uint32_t *thr_tab; // same shape, ceil(eps*2^24)
   const double *u;         // replay draws of iteration j+1 (or nullptr)
   const uint8_t *b;
+  // TD rule (general kernel only): 0 Q-learning, 1 SARSA, 2 Expected SARSA (algorithms.py:96-234)
+  int algo;
+  const double *u2, *u3;   // SARSA: replayed draws of iteration j for the update's next action
+  const uint8_t *b2, *b3;  //        (spgg.py:433) and for the NI statistic's (spgg.py:452); or nullptr
   int j;                   // absolute iteration index this launch finishes (state index)
   int rel;                 // j - (iteration at start of the spgg_step call)
   int cap;                 // rows per replica in stats/gmax tables
@@ -543,6 +547,9 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
     else inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));
   }
   const long long tab_idx = (long long)(a.rel + 1) * g.n_rep + rep;
+  // SARSA / Expected SARSA evaluate the policy of the iteration being finished (epsilon_j)
+  const double eps_u = (upd && a.algo != 0) ? a.eps_tab[(long long)a.rel * g.n_rep + rep] : 0.0;
+  const uint32_t thr_u = (upd && a.algo == 1) ? a.thr_tab[(long long)a.rel * g.n_rep + rep] : 0u;
   const uint32_t thr = sel ? a.thr_tab[tab_idx] : 0u;
   const double eps = (sel && REPLAY) ? a.eps_tab[tab_idx] : 0.0;
 
@@ -616,6 +623,23 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
           w4[k4] = sel4<uint32_t>(lane & 3, x0, x1, x2, x3);
         }
       }
+      uint32_t wS1[4] = {0, 0, 0, 0}, wS2[4] = {0, 0, 0, 0};
+      if (upd && a.algo == 1 && a.u2 == nullptr) {
+        // SARSA's two further draws of iteration j: Philox streams 1 and 2 (counter word 3)
+#pragma unroll
+        for (int st = 1; st <= 2; ++st) {
+          uint32_t wc[4];
+          philox4x32_10((uint32_t)((c0 >> 2) + lane), (uint32_t)(g.row0 + i), (uint32_t)a.j, (uint32_t)st,
+                        rc.seed_lo, rc.seed_hi, wc);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int src = 8 * k4 + (lane >> 2);
+            const uint32_t x0 = __shfl_sync(0xffffffffu, wc[0], src), x1 = __shfl_sync(0xffffffffu, wc[1], src);
+            const uint32_t x2 = __shfl_sync(0xffffffffu, wc[2], src), x3 = __shfl_sync(0xffffffffu, wc[3], src);
+            (st == 1 ? wS1 : wS2)[k4] = sel4<uint32_t>(lane & 3, x0, x1, x2, x3);
+          }
+        }
+      }
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
         const int cc = k4 * 32 + lane;
@@ -665,8 +689,30 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
             const QT qe = sel4<QT>(e, q0_, q1_, q2_, q3_);
             const QT na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
             QT qtd, qfin;
+            // SARSA: the eps-greedy draws that pick the next action (update, then NI statistic)
+            bool ex1 = false, ex2 = false;
+            int rn1 = 0, rn2 = 0;
+            if (a.algo == 1) {
+              if (a.u2 != nullptr) {
+                ex1 = a.u2[site] < eps_u; rn1 = a.b2[site];
+                ex2 = a.u3[site] < eps_u; rn2 = a.b3[site];
+              } else {
+                ex1 = (wS1[k4] >> 8) < thr_u; rn1 = (int)(wS1[k4] & 1u);
+                ex2 = (wS2[k4] >> 8) < thr_u; rn2 = (int)(wS2[k4] & 1u);
+              }
+            }
             if constexpr (Md::kFp64) {
-              const double mx = fmax(na, nb);
+              // value of the next state: max (algorithms.py:125), Q[s'][a'] (:169) or the
+              // eps-greedy expectation p0*Q[s'][0] + p1*Q[s'][1] (:212-224)
+              auto next_value = [&](double x0, double x1, bool ex, int rn) -> double {
+                if (a.algo == 0) return fmax(x0, x1);
+                const int greedy = (x1 > x0) ? 1 : 0;
+                if (a.algo == 1) return (ex ? rn : greedy) ? x1 : x0;
+                const double po = __ddiv_rn(eps_u, 2.0);
+                const double pg = __dadd_rn(__dsub_rn(1.0, eps_u), po);
+                return __dadd_rn(__dmul_rn(greedy ? po : pg, x0), __dmul_rn(greedy ? pg : po, x1));
+              };
+              const double mx = next_value(na, nb, ex1, rn1);
               const double td = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, mx)), qe);  // algorithms.py:128
               qtd = __dadd_rn(qe, __dmul_rn(rc.alpha, td));                              // algorithms.py:131
               const double lam = __ddiv_rn(__dmul_rn(rc.kappa, fmax(0.0, best)), den);   // spgg.py:489
@@ -674,7 +720,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
               // TD error on the table after the TD write (spgg.py:446-473)
               const double na2 = (s_new == s && act == 0) ? qtd : na;
               const double nb2 = (s_new == s && act == 1) ? qtd : nb;
-              const double td2 = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, fmax(na2, nb2))), qtd);
+              const double td2 = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, next_value(na2, nb2, ex2, rn2))), qtd);
               qfin = __dadd_rn(qtd, nu);                                                 // spgg.py:509
               const double an = fabs(nu);
               sumNI += __dmul_rn(
@@ -692,14 +738,21 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
                 sumRewD += vx;
               }
             } else {
-              const float mx = fmaxf(na, nb);
+              auto next_value = [&](float x0, float x1, bool ex, int rn) -> float {
+                if (a.algo == 0) return fmaxf(x0, x1);
+                const int greedy = (x1 > x0) ? 1 : 0;
+                if (a.algo == 1) return (ex ? rn : greedy) ? x1 : x0;
+                const float e = (float)eps_u, po = __fmul_rn(e, 0.5f), pg = __fadd_rn(__fsub_rn(1.0f, e), po);
+                return __fmaf_rn(greedy ? pg : po, x1, __fmul_rn(greedy ? po : pg, x0));
+              };
+              const float mx = next_value(na, nb, ex1, rn1);
               const float td = __fsub_rn(__fmaf_rn(rc.gamma_f, mx, vx), qe);
               qtd = __fmaf_rn(rc.alpha_f, td, qe);
               const float lam = __fmul_rn(__fmul_rn(rc.kappa_f, fmaxf(0.0f, best)), inv_den);
               const float nu = same ? lam : -lam;
               const float na2 = (s_new == s && act == 0) ? qtd : na;
               const float nb2 = (s_new == s && act == 1) ? qtd : nb;
-              const float td2 = __fsub_rn(__fmaf_rn(rc.gamma_f, fmaxf(na2, nb2), vx), qtd);
+              const float td2 = __fsub_rn(__fmaf_rn(rc.gamma_f, next_value(na2, nb2, ex2, rn2), vx), qtd);
               qfin = __fadd_rn(qtd, nu);
               const float an = fabsf(nu);
               tni += __fdividef(an, fabsf(rc.alpha_f * td2) + an + 1e-8f) * 100.0f;

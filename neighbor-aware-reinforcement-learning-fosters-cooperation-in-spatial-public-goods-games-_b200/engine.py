@@ -12,7 +12,9 @@ import numpy as np
 
 from . import _lib as L_
 
-_ALGOS = {"qlearning": L_.ALGO_QLEARNING, "q-learning": L_.ALGO_QLEARNING}
+_ALGOS = {"qlearning": L_.ALGO_QLEARNING, "q-learning": L_.ALGO_QLEARNING,
+          "sarsa": L_.ALGO_SARSA,
+          "expected_sarsa": L_.ALGO_EXPECTED_SARSA, "expected-sarsa": L_.ALGO_EXPECTED_SARSA}
 
 
 def params_struct(p: dict, seed: int = 0, precision: str = "fp32", rows=None, row0: int = 0,
@@ -26,10 +28,9 @@ def params_struct(p: dict, seed: int = 0, precision: str = "fp32", rows=None, ro
                          f"Must be 'reputation' or 'action'")
     algo = str(p.get("algorithm", "qlearning")).lower()
     if algo not in _ALGOS:
-        if algo in ("sarsa", "expected_sarsa", "expected-sarsa", "double_qlearning",
-                    "double-q-learning"):
+        if algo in ("double_qlearning", "double-q-learning"):
             raise ValueError(f"algorithm '{algo}' is not built into the fused CUDA step yet "
-                             "(only 'qlearning'); there is no CPU fallback")
+                             "(two Q tables); there is no CPU fallback")
         # same message as algorithms.py:382-383
         raise ValueError(f"Unknown algorithm: {algo}. "
                          f"Supported: 'qlearning', 'sarsa', 'expected_sarsa', 'double_qlearning'")
@@ -122,6 +123,10 @@ class Engine:
         arrays for the next n iterations (algorithms.py:105,108)."""
         u = np.ascontiguousarray(u, dtype=np.float64)
         b = np.ascontiguousarray(b, dtype=np.uint8)
+        if u.ndim == 4:   # (n, pairs, rows, L): SARSA draws three pairs per iteration
+            L_.check(self.lib.spgg_set_replay_pairs(self._h, u.shape[0], u.shape[1], u.ctypes.data,
+                                                    b.ctypes.data))
+            return
         n = u.shape[0] if u.ndim == 3 else 0
         L_.check(self.lib.spgg_set_replay(self._h, n, u.ctypes.data if n else None,
                                           b.ctypes.data if n else None))

@@ -129,7 +129,8 @@ class SPGG:
         if getattr(self.algorithm, "kernel_tag", None) is None:
             raise ValueError(
                 f"algorithm '{getattr(self.algorithm, 'name', type(self.algorithm).__name__)}' is not "
-                "built into the fused CUDA step (only Q-learning is); there is no CPU fallback")
+                "built into the fused CUDA step (Q-learning, SARSA and Expected SARSA are); "
+                "there is no CPU fallback")
 
     def _snapshot(self, eng, i, data_file, snaps, replica=0):
         """State before iteration i acts (spgg.py:397-402)."""
@@ -193,7 +194,7 @@ def run_models(models, filenames):
     if draws == "numpy":
         if n != 1:
             raise ValueError("draws='numpy' (replay of the reference's stream) runs one model at a time")
-        chunk_max = max(1, min(chunk_max, (64 << 20) // (9 * N) or 1))
+        chunk_max = max(1, min(chunk_max, (64 << 20) // (27 * N) or 1))
     eps0 = [float(m.algorithm.epsilon) for m in models]
     for m in models:
         snapshots_dir = os.path.join(m.folder, 'plots', 'snapshots') if m.folder else 'snapshots'
@@ -222,12 +223,16 @@ def run_models(models, filenames):
             nxt = min([c for c in cut_points if c > t] + [T])
             k_req = min(nxt - t, chunk_max)
             if draws == "numpy":
-                u = np.empty((k_req, L, L))
-                b = np.empty((k_req, L, L), np.uint8)
-                for i in range(k_req):                                  # algorithms.py:105,108
-                    u[i] = m0._rng.rand(L, L)
-                    b[i] = m0._rng.randint(0, 2, size=(L, L))
-                eng.set_replay(u, b)
+                # the reference's stream: per iteration rand(L,L) then randint(0,2,(L,L))
+                # (algorithms.py:105,108); SARSA draws three such pairs (spgg.py:410,433,452)
+                pairs = 3 if getattr(m0.algorithm, "kernel_tag", "") == "sarsa" else 1
+                u = np.empty((k_req, pairs, L, L))
+                b = np.empty((k_req, pairs, L, L), np.uint8)
+                for i in range(k_req):
+                    for q in range(pairs):
+                        u[i, q] = m0._rng.rand(L, L)
+                        b[i, q] = m0._rng.randint(0, 2, size=(L, L))
+                eng.set_replay(u if pairs > 1 else u[:, 0], b if pairs > 1 else b[:, 0])
             eng.step(k_req)
             for r, m in enumerate(models):
                 if stopped[r]:

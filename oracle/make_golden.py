@@ -80,8 +80,33 @@ KEEP_DATASETS = (
 )
 
 
+TD_CASES = {
+    # other TD rules of algorithms.py (reference CI matrix, run-experiments.yml:17)
+    "sarsa_rep_m1": dict(RUNNER_FIXED, L=12, iterations=30, r=3.0, influence_factor=1.0,
+                         use_second_order=False, reward_weight_payoff=0.95, rep_gain_C=1.0,
+                         state_representation="reputation", algorithm="sarsa"),
+    "sarsa_act_m2": dict(RUNNER_FIXED, L=12, iterations=30, r=4.0, influence_factor=0.5,
+                         use_second_order=True, reward_weight_payoff=1.0, rep_gain_C=1.0,
+                         state_representation="action", algorithm="sarsa"),
+    "expsarsa_rep_m2": dict(RUNNER_FIXED, L=12, iterations=30, r=3.6, influence_factor=1.0,
+                            use_second_order=True, reward_weight_payoff=0.95, rep_gain_C=0.5,
+                            state_representation="reputation", algorithm="expected_sarsa"),
+    "expsarsa_act_m1": dict(RUNNER_FIXED, L=14, iterations=30, r=4.0, influence_factor=1.0,
+                            use_second_order=False, reward_weight_payoff=1.0, rep_gain_C=1.0,
+                            state_representation="action", algorithm="expected_sarsa"),
+}
+
+
 def make_replay(name, params, seed):
     out = ref_harness.run_reference(seed, **params)
+    if "u" not in out:
+        # rules that draw more than one pair per iteration (SARSA: 3 pairs, spgg.py:410,433,452):
+        # keep the stream as (n_steps, pairs, L, L)
+        n, L = out["n_steps"], params["L"]
+        pairs = len(out["rand"]) // max(n, 1)
+        assert pairs * n == len(out["rand"]) == len(out["randint"])
+        out["u"] = np.stack(out["rand"]).reshape(n, pairs, L, L)
+        out["b"] = np.stack(out["randint"]).astype(np.uint8).reshape(n, pairs, L, L)
     blob = dict(params_json=np.array(json.dumps(params)), seed=np.array(seed),
                 q0=out["q0"], s0=out["s0"].astype(np.uint8), u=out["u"], b=out["b"],
                 q_final=out["q_final"], r_final=out["r_final"],
@@ -122,6 +147,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-band", action="store_true")
     ap.add_argument("--no-replay", action="store_true")
+    ap.add_argument("--td", action="store_true", help="also (re)write the SARSA / Expected-SARSA fixtures")
     ap.add_argument("--seeds", type=int, default=8)
     ap.add_argument("--procs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
     a = ap.parse_args()
@@ -129,6 +155,9 @@ def main():
     if not a.no_replay:
         for i, (name, p) in enumerate(REPLAY_CASES.items()):
             print("wrote", make_replay(name, p, 7 + i))
+    if a.td:
+        for i, (name, p) in enumerate(TD_CASES.items()):
+            print("wrote", make_replay(name, p, 40 + i))
     if not a.no_band:
         make_bands(a.seeds, a.procs)
 

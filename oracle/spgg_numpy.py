@@ -86,9 +86,31 @@ def epsilon_sequence(eps0, decay, eps_min, n):
     return used, after
 
 
-def qlearning_step(S, R, Q, eps, u, b, p):
+def _td_target(Qtab, ii, jj, s_new, algo, eps, u, b):
+    """Value of the next state used by the TD error, per rule:
+    qlearning  max_a Q[s',a]                                   algorithms.py:125
+    sarsa      Q[s',a'] with a' drawn eps-greedily from Q[s']   algorithms.py:142-150,169 (draws u, b)
+    expected_sarsa  sum_a pi(a|s') Q[s',a], pi eps-greedy       algorithms.py:212-224"""
+    row = Qtab[ii, jj, s_new, :]
+    if algo == "qlearning":
+        return np.max(row, axis=2)
+    greedy = np.argmax(row, axis=2)
+    if algo == "sarsa":
+        a_next = np.where(u < eps, b.astype(np.int64), greedy)
+        return Qtab[ii, jj, s_new, a_next]
+    if algo == "expected_sarsa":
+        probs = np.full(row.shape, eps / 2)
+        probs[ii, jj, greedy] = (1 - eps) + eps / 2
+        return np.sum(probs * row, axis=2)
+    raise ValueError(f"oracle: algorithm {algo!r} not restated")
+
+
+def qlearning_step(S, R, Q, eps, u, b, p, algo="qlearning", extra=None):
     """One full iteration of spgg.py:368-592 for the Q-learning rule
-    (algorithms.py:96-133).  ``u``/``b`` are that iteration's draw arrays.
+    (algorithms.py:96-133) - or, with ``algo`` = 'sarsa' / 'expected_sarsa', the rules of
+    algorithms.py:136-234 as spgg.py:431-473 applies them.  ``u``/``b`` are the iteration's
+    action draws; ``extra`` = ((u2, b2), (u3, b3)) are SARSA's two further draw pairs
+    (next action for the update, spgg.py:433, and for the NI statistic, spgg.py:452).
     Returns (S', R', Q', stats dict).  Q is updated on a copy."""
     L = S.shape[0]
     M = 2 if p["use_second_order"] else 1
@@ -130,13 +152,15 @@ def qlearning_step(S, R, Q, eps, u, b, p):
 
     Q2 = Q.copy()
     q0 = Q[ii, jj, s_old, a]
-    nxt = np.max(Q[ii, jj, s_new, :], axis=2)
+    x1 = extra[0] if extra else (None, None)
+    x2 = extra[1] if extra else (None, None)
+    nxt = _td_target(Q, ii, jj, s_new, algo, eps, *x1)
     td = rew + gamma * nxt - q0                                   # algorithms.py:128
     Q2[ii, jj, s_old, a] = q0 + alpha * td                        # algorithms.py:131
 
     # TD error on the updated table, only feeds the NI statistic (spgg.py:446-473)
     q_cur = Q2[ii, jj, s_old, a]
-    td2 = rew + gamma * np.max(Q2[ii, jj, s_new, :], axis=2) - q_cur
+    td2 = rew + gamma * _td_target(Q2, ii, jj, s_new, algo, eps, *x2) - q_cur
 
     diffs = np.stack([at(rew, di, dj) - rew for (di, dj) in offs])  # spgg.py:486
     best = diffs.max(axis=0)
@@ -208,8 +232,13 @@ def simulate(p, S0, R0, Q0, draws):
             break
         if t in SNAPSHOT_ITERS:
             snaps[t] = (R.copy(), S.copy())
-        u, b = draws(t, L)
-        S, R, Q, st = qlearning_step(S, R, Q, eps, u, b, p)
+        algo = str(p.get("algorithm", "qlearning")).lower()
+        if algo == "sarsa":      # three draw pairs per iteration (spgg.py:410, 433, 452)
+            u, b, u2, b2, u3, b3 = draws(t, L)
+            S, R, Q, st = qlearning_step(S, R, Q, eps, u, b, p, algo, ((u2, b2), (u3, b3)))
+        else:
+            u, b = draws(t, L)
+            S, R, Q, st = qlearning_step(S, R, Q, eps, u, b, p, algo)
         P_last = st["P"]
         eps = max(eps * p["epsilon_decay"], p["epsilon_min"])
         push("coop_rate_history", st["coop_rate"])

@@ -108,12 +108,86 @@ def test_philox_stream_stays_in_the_reference_seed_band(golden_dir, cfg):
         eng.close()
 
 
-def test_other_td_rules_fail_loudly(tmp_path):
+def test_unbuilt_td_rule_fails_loudly(tmp_path):
     import spgg_b200
-    for algo in ("sarsa", "expected_sarsa", "double_qlearning"):
-        m = spgg_b200.SPGG(L=16, iterations=3, algorithm=algo, seed=1)
-        with pytest.raises(ValueError, match="no CPU fallback"):
-            m.run(str(tmp_path / "x.h5"))
+    m = spgg_b200.SPGG(L=16, iterations=3, algorithm="double_qlearning", seed=1)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        m.run(str(tmp_path / "x.h5"))
+
+
+TD_GOLDEN = ["sarsa_rep_m1", "sarsa_act_m2", "expsarsa_rep_m2", "expsarsa_act_m1"]
+
+
+@pytest.mark.parametrize("name", TD_GOLDEN)
+def test_sarsa_and_expected_sarsa_replay_the_reference(tmp_path, golden_dir, name):
+    """algorithms.py:136-234 as applied by spgg.py:431-473: fp64 instantiation + the reference's
+    own draw stream (SARSA: three pairs per iteration) == the reference run, bit for bit."""
+    import spgg_b200
+    z, p = load_golden(golden_dir, name)
+    m = spgg_b200.SPGG(**p, seed=int(z["seed"]), precision="fp64", draws="numpy")
+    m.folder = str(tmp_path)
+    ret = m.run(str(tmp_path / "run.h5"))
+    assert np.array_equal(m._Sn, z["s_final"])
+    assert np.array_equal(m.R, z["r_final"])
+    assert np.array_equal(m.q_table, z["q_final"])
+    np.testing.assert_allclose(ret, z["ret"], rtol=1e-12)
+    got = _read(str(tmp_path / "run.h5"))
+    for k in [f[3:] for f in z.files if f.startswith("ds_")]:
+        want = z["ds_" + k]
+        if want.dtype.kind == "i":
+            assert np.array_equal(got[k], want), k
+        else:
+            np.testing.assert_allclose(got[k], want, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+
+
+@pytest.mark.parametrize("algo", ["sarsa", "expected_sarsa"])
+def test_td_rules_engine_vs_numpy_oracle(algo):
+    """Direct engine check at a larger size against the NumPy restatement (pinned to the
+    reference by the fixtures above): L=48, 60 iterations, both neighbour orders."""
+    import spgg_b200
+    from oracle import spgg_numpy
+    from helpers import full_params
+    for second, state in ((False, "reputation"), (True, "action")):
+        L, n = 48, 60
+        p = full_params(dict(C1, L=L, use_second_order=second, state_representation=state, algorithm=algo,
+                             iterations=n))
+        rs = np.random.RandomState(3)
+        Q0 = rs.uniform(-0.01, 0.01, (L, L, 2, 2))
+        S0 = rs.randint(0, 2, (L, L))
+        pairs = 3 if algo == "sarsa" else 1
+        u = rs.rand(n, pairs, L, L)
+        b = rs.randint(0, 2, (n, pairs, L, L)).astype(np.uint8)
+        eng = spgg_b200.Engine(p, precision="fp64")
+        eng.set_state(S0, np.zeros((L, L)), Q0)
+        eng.set_replay(u if pairs > 1 else u[:, 0], b if pairs > 1 else b[:, 0])
+        eng.step(n)
+        S, R, Q = eng.get_state()
+        draws = (lambda t, L_: tuple(x for k in range(3) for x in (u[t - 1, k], b[t - 1, k]))) if pairs == 3 \
+            else (lambda t, L_: (u[t - 1, 0], b[t - 1, 0]))
+        ref = spgg_numpy.simulate(p, S0, np.zeros((L, L)), Q0, draws)
+        assert np.array_equal(S, ref["Sn_final"]) and np.array_equal(R, ref["R_final"])
+        assert np.array_equal(Q, ref["q_final"])
+        rows = eng.stats()[1:]
+        np.testing.assert_allclose(rows[:, 30] / (L * L), ref["neighbor_influence_percent"], rtol=1e-9)
+        eng.close()
+
+
+@pytest.mark.parametrize("algo", ["sarsa", "expected_sarsa"])
+def test_td_rules_throughput_mode_runs_and_is_reproducible(tmp_path, algo):
+    """fp32 + Philox (streams 0/1/2 for SARSA) through the class: same seed -> same files."""
+    import spgg_b200
+    outs = []
+    for k in range(2):
+        m = spgg_b200.SPGG(L=96, iterations=150, r=3.0, cost=1, alpha=0.8, epsilon_decay=0.99,
+                           use_second_order=False, reward_weight_payoff=0.95, rep_gain_C=1.0,
+                           algorithm=algo, seed=11)
+        m.folder = str(tmp_path / str(k))
+        m.run(str(tmp_path / f"{k}.h5"))
+        outs.append(_read(str(tmp_path / f"{k}.h5")))
+    for key in ("Sn_final", "R_final", "coop_rate_history", "switch_C_to_D"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+    fc = outs[0]["coop_rate_history"]
+    assert len(fc) == 150 and 0.0 < fc[-1] < 1.0
 
 
 def test_gpu_runner_batches_equal_single_experiments(tmp_path):

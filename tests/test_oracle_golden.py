@@ -212,3 +212,32 @@ def test_early_exit_series_lengths():
     out = spgg_numpy.simulate(p, np.zeros((L, L), np.int64), np.zeros((L, L)),
                               np.zeros((L, L, 2, 2)), lambda t, L_: (None, None))
     assert len(out["coop_rate_history"]) == 1 and "epsilon_history_final" not in out
+
+
+TD_GOLDEN = ["sarsa_rep_m1", "sarsa_act_m2", "expsarsa_rep_m2", "expsarsa_act_m1"]
+
+
+def _td_draws(z):
+    u, b = z["u"], z["b"]
+    if u.ndim == 4:      # (n, pairs, L, L): SARSA draws three pairs per iteration
+        return lambda t, L: tuple(x for k in range(u.shape[1]) for x in (u[t - 1, k], b[t - 1, k]))
+    return lambda t, L: (u[t - 1], b[t - 1])
+
+
+@pytest.mark.parametrize("name", TD_GOLDEN)
+def test_numpy_oracle_other_td_rules_reproduce_reference(golden_dir, name):
+    """SARSA (three draw pairs per iteration, spgg.py:410,433,452) and Expected SARSA
+    (algorithms.py:197-234) against the executed reference, bit for bit."""
+    from oracle import spgg_numpy
+    z, p = load_golden(golden_dir, name)
+    p = full_params(p)
+    L, n = p["L"], int(z["u"].shape[0])
+    assert (z["u"].ndim == 4 and z["u"].shape[1] == 3) == (p["algorithm"] == "sarsa")
+    out = spgg_numpy.simulate(dict(p, iterations=n), z["s0"].astype(np.int64), np.zeros((L, L)),
+                              z["q0"], _td_draws(z))
+    assert np.array_equal(out["Sn_final"], z["s_final"])
+    assert np.array_equal(out["R_final"], z["r_final"])
+    assert np.array_equal(out["q_final"], z["q_final"])
+    for key in ("coop_rate_history", "switch_C_to_D", "neighbor_influence_percent",
+                "avg_q_s0_c_history", "cooperators_q_s0_d_history"):
+        assert np.array_equal(out[key], z["ds_" + key], equal_nan=True), key
