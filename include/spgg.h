@@ -43,6 +43,7 @@ extern "C" {
 #define SPGG_ALGO_QLEARNING 0
 #define SPGG_ALGO_SARSA 1          /* algorithms.py:136-178, applied as spgg.py:431-438,450-454 */
 #define SPGG_ALGO_EXPECTED_SARSA 2 /* algorithms.py:181-234, spgg.py:455-463 */
+#define SPGG_ALGO_DOUBLE_QLEARNING 3 /* algorithms.py:237-341, spgg.py:464-468,498-505: two tables per site */
 
 /* reputation storage in fp32 mode */
 #define SPGG_RSTORE_AUTO 0 /* int8 when rep_gain_C, delta_R_D, R_min, R_max are multiples of 2^-k that fit */
@@ -117,7 +118,9 @@ void spgg_destroy(spgg_t *h);
 
 /* Upload q_table (rows*L*2*2 doubles, layout of spgg.py:121), R (rows*L
  * doubles, spgg.py:129) and _Sn (rows*L bytes, 0=C 1=D, spgg.py:162) of one
- * replica.  Resets that replica's iteration counter and epsilon. */
+ * replica.  Resets that replica's iteration counter and epsilon.
+ * SPGG_ALGO_DOUBLE_QLEARNING: Q holds both tables, rows*L*2*2*2 doubles laid out
+ * [site][table][state][action] (q_table_1, q_table_2 of algorithms.py:245-260). */
 int spgg_set_state(spgg_t *h, int replica, const uint8_t *S, const double *R, const double *Q);
 int spgg_get_state(spgg_t *h, int replica, uint8_t *S, double *R, double *Q);
 
@@ -134,7 +137,9 @@ int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const uint8_t *b);
 /* Same with n_pairs (rand, randint) pairs per iteration, arrays laid out
  * (n_steps, n_pairs, rows, L): SARSA consumes three pairs per iteration - the action
  * (algorithms.py:145-148 via spgg.py:410), the next action of the update (spgg.py:433) and
- * the next action of the NI statistic (spgg.py:452); every other rule consumes one. */
+ * the next action of the NI statistic (spgg.py:452); Double Q-learning consumes two (the
+ * action, and rand(L,L) < 0.5 choosing the table to update, algorithms.py:303 - the second
+ * pair's b is ignored); every other rule consumes one. */
 int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const double *u, const uint8_t *b);
 
 /* Run n_steps iterations of the loop body spgg.py:368-592 for all replicas

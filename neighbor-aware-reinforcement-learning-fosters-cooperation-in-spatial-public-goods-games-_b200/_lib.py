@@ -25,7 +25,7 @@ ST_SUM_NI, ST_N_BEST_POS, ST_N_BEST_2ND, ST_GMAX = 30, 31, 32, 33
 
 PREC_FP32, PREC_FP64 = 0, 1
 STATE_REPUTATION, STATE_ACTION = 0, 1
-ALGO_QLEARNING, ALGO_SARSA, ALGO_EXPECTED_SARSA = 0, 1, 2
+ALGO_QLEARNING, ALGO_SARSA, ALGO_EXPECTED_SARSA, ALGO_DOUBLE_QLEARNING = 0, 1, 2, 3
 RSTORE_AUTO, RSTORE_INT8, RSTORE_FP32 = 0, 1, 2
 E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4
 

@@ -61,14 +61,28 @@ class ExpectedSARSA(RLAlgorithm):
 
 
 class DoubleQLearning(RLAlgorithm):
-    """Two tables, cross-evaluated (algorithms.py:292-341); not yet compiled into the
-    fused step."""
+    """Two tables; a fair draw per site picks the one to update, its target comes from the
+    other (algorithms.py:292-341); the policy and the statistics use their mean (:263)."""
+    kernel_tag = "double_qlearning"
     name = "double_qlearning"
 
     def __init__(self, alpha, gamma, epsilon, epsilon_decay, epsilon_min, **kwargs):
         super().__init__(alpha, gamma, epsilon, epsilon_decay, epsilon_min, **kwargs)
         self.q_table_1 = None
         self.q_table_2 = None
+
+    def initialize_q_tables(self, shape, rng=None):
+        """algorithms.py:249-260 (two uniform(-0.01, 0.01) draws, table 1 first)."""
+        import numpy as np
+        rng = np.random if rng is None else rng
+        self.q_table_1 = rng.uniform(low=-0.01, high=0.01, size=shape)
+        self.q_table_2 = rng.uniform(low=-0.01, high=0.01, size=shape)
+
+    def get_combined_q_table(self):
+        """algorithms.py:262-266."""
+        if self.q_table_1 is None or self.q_table_2 is None:
+            raise ValueError("Q-tables not initialized. Call initialize_q_tables first.")
+        return (self.q_table_1 + self.q_table_2) / 2
 
 
 _FACTORY = {

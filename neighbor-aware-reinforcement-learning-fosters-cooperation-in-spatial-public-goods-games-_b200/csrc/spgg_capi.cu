@@ -94,6 +94,7 @@ struct spgg_handle {
   size_t elem_R() const { return mode == MODE_F64 ? 8 : (mode == MODE_F32_F ? 4 : 1); }
   size_t elem_Q() const { return mode == MODE_F64 ? 8 : 4; }
   size_t elem_val() const { return mode == MODE_F64 ? 8 : 4; }
+  int nq() const { return params[0].algorithm == SPGG_ALGO_DOUBLE_QLEARNING ? 8 : 4; }  // Q values per site
 };
 
 // ---------------------------------------------------------------- constants
@@ -293,7 +294,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   if (p0.precision != SPGG_PREC_FP32 && p0.precision != SPGG_PREC_FP64)
     return fail(SPGG_E_INVALID, "unknown precision %d", p0.precision);
   if (p0.algorithm != SPGG_ALGO_QLEARNING && p0.algorithm != SPGG_ALGO_SARSA &&
-      p0.algorithm != SPGG_ALGO_EXPECTED_SARSA)
+      p0.algorithm != SPGG_ALGO_EXPECTED_SARSA && p0.algorithm != SPGG_ALGO_DOUBLE_QLEARNING)
     return fail(SPGG_E_UNSUPPORTED, "algorithm code %d is not built into the fused kernel", p0.algorithm);
   if (p0.row0 < 0 || p0.row0 + p0.rows > p0.L) return fail(SPGG_E_INVALID, "row0/rows outside the lattice");
   for (int r = 1; r < n_replicas; ++r) {
@@ -387,7 +388,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   // the fast kernel's packed 16-bit counters bound the sites one thread may visit per launch
   if (h->fast && (g.site_stride / ((long long)g.ctas_per_rep * FTHREADS)) > 60000) h->fast = false;
 
-  const size_t nQ = (size_t)n_replicas * g.site_stride * 4 * h->elem_Q();
+  const size_t nQ = (size_t)n_replicas * g.site_stride * h->nq() * h->elem_Q();
   const size_t nR = (size_t)n_replicas * g.plane_stride * h->elem_R();
   const size_t nC = (size_t)n_replicas * g.plane_stride * h->elem_code();
   const size_t nS = (size_t)n_replicas * g.bits_stride * 4;
@@ -498,7 +499,7 @@ static int ensure_scratch(spgg_handle *h, bool want_q) {
     CUDA_TRY(cudaMalloc((void **)&h->d_sc_R, n * sizeof(double)));
     CUDA_TRY(cudaMalloc((void **)&h->d_sc_info, 2 * sizeof(unsigned long long)));
   }
-  if (want_q && !h->d_sc_Q) CUDA_TRY(cudaMalloc((void **)&h->d_sc_Q, n * 4 * sizeof(double)));
+  if (want_q && !h->d_sc_Q) CUDA_TRY(cudaMalloc((void **)&h->d_sc_Q, n * h->nq() * sizeof(double)));
   return SPGG_OK;
 }
 
@@ -519,10 +520,10 @@ extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double
     const size_t n = (size_t)nr * g.L, off = (size_t)i0 * g.L;
     CUDA_TRY(cudaMemcpyAsync(h->d_sc_S, S + off, n, cudaMemcpyHostToDevice, 0));
     CUDA_TRY(cudaMemcpyAsync(h->d_sc_R, R + off, n * sizeof(double), cudaMemcpyHostToDevice, 0));
-    CUDA_TRY(cudaMemcpyAsync(h->d_sc_Q, Q + off * 4, n * 4 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_sc_Q, Q + off * h->nq(), n * h->nq() * sizeof(double), cudaMemcpyHostToDevice, 0));
     const int grid = (int)std::min<long long>(148 * 16, ((long long)nr * ((g.L + 31) / 32) * 32 + 255) / 256);
 #define IMPORT(Md) k_import_rows<Md><<<std::max(1, grid), 256>>>(g, rep, i0, nr, h->d_sc_S, h->d_sc_R, h->d_sc_Q, \
-                       h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->d_sc_info)
+                       h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->d_sc_info, h->nq())
     if (h->mode == MODE_F32_I8) IMPORT(ModeF32I8);
     else if (h->mode == MODE_F32_F) IMPORT(ModeF32F);
     else IMPORT(ModeF64);
@@ -561,7 +562,7 @@ extern "C" int spgg_get_state(spgg_t *h, int rep, uint8_t *S, double *R, double 
     const size_t n = (size_t)nr * g.L, off = (size_t)i0 * g.L;
     const int grid = (int)std::min<long long>(148 * 16, ((long long)n + 255) / 256);
 #define EXPORT(Md) k_export_rows<Md><<<std::max(1, grid), 256>>>(g, rep, i0, nr, S ? h->d_sc_S : nullptr, \
-                       R ? h->d_sc_R : nullptr, Q ? h->d_sc_Q : nullptr, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq)
+                       R ? h->d_sc_R : nullptr, Q ? h->d_sc_Q : nullptr, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->nq())
     if (h->mode == MODE_F32_I8) EXPORT(ModeF32I8);
     else if (h->mode == MODE_F32_F) EXPORT(ModeF32F);
     else EXPORT(ModeF64);
@@ -570,7 +571,7 @@ extern "C" int spgg_get_state(spgg_t *h, int rep, uint8_t *S, double *R, double 
     h->launches += 1;
     if (S) CUDA_TRY(cudaMemcpyAsync(S + off, h->d_sc_S, n, cudaMemcpyDeviceToHost, 0));
     if (R) CUDA_TRY(cudaMemcpyAsync(R + off, h->d_sc_R, n * sizeof(double), cudaMemcpyDeviceToHost, 0));
-    if (Q) CUDA_TRY(cudaMemcpyAsync(Q + off * 4, h->d_sc_Q, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    if (Q) CUDA_TRY(cudaMemcpyAsync(Q + off * h->nq(), h->d_sc_Q, n * h->nq() * sizeof(double), cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
   }
   return SPGG_OK;
@@ -582,9 +583,10 @@ extern "C" int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const ui
 
 extern "C" int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const double *u, const uint8_t *b) {
   if (!h) return fail(SPGG_E_INVALID, "null handle");
-  if (n_steps > 0 && n_pairs != (h->params[0].algorithm == SPGG_ALGO_SARSA ? 3 : 1))
-    return fail(SPGG_E_INVALID, "this TD rule consumes %d draw pair(s) per iteration, got %d",
-                h->params[0].algorithm == SPGG_ALGO_SARSA ? 3 : 1, n_pairs);
+  const int want_pairs = h->params[0].algorithm == SPGG_ALGO_SARSA ? 3
+                         : (h->params[0].algorithm == SPGG_ALGO_DOUBLE_QLEARNING ? 2 : 1);
+  if (n_steps > 0 && n_pairs != want_pairs)
+    return fail(SPGG_E_INVALID, "this TD rule consumes %d draw pair(s) per iteration, got %d", want_pairs, n_pairs);
   if (h->n_rep != 1) return fail(SPGG_E_UNSUPPORTED, "replay draws are supported for a single replica");
   int rcode = finish_pending(h);
   if (rcode) return rcode;
@@ -684,11 +686,11 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   a.algo = h->params[0].algorithm;
   // SARSA: pairs 1 and 2 of iteration j (entry j-1-replay_first) feed the update launched now
   const long long ue = j - 1 - h->replay_first;
-  const bool upd_replay = do_update && a.algo == SPGG_ALGO_SARSA && h->d_u && np_ == 3 && ue >= 0 && ue < h->replay_n;
-  a.u2 = upd_replay ? h->d_u + ((size_t)ue * 3 + 1) * ss : nullptr;
-  a.b2 = upd_replay ? h->d_b + ((size_t)ue * 3 + 1) * ss : nullptr;
-  a.u3 = upd_replay ? h->d_u + ((size_t)ue * 3 + 2) * ss : nullptr;
-  a.b3 = upd_replay ? h->d_b + ((size_t)ue * 3 + 2) * ss : nullptr;
+  const bool upd_replay = do_update && np_ >= 2 && h->d_u && ue >= 0 && ue < h->replay_n;
+  a.u2 = upd_replay ? h->d_u + ((size_t)ue * np_ + 1) * ss : nullptr;   // SARSA next action / Double-Q table choice
+  a.b2 = upd_replay ? h->d_b + ((size_t)ue * np_ + 1) * ss : nullptr;
+  a.u3 = (upd_replay && np_ == 3) ? h->d_u + ((size_t)ue * 3 + 2) * ss : nullptr;
+  a.b3 = (upd_replay && np_ == 3) ? h->d_b + ((size_t)ue * 3 + 2) * ss : nullptr;
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
 #ifdef SPGG_TRACE
@@ -803,9 +805,9 @@ extern "C" int spgg_init_random(spgg_t *h, int rep, uint64_t seed) {
   CUDA_TRY(cudaSetDevice(h->device));
   const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
   const int grid = 148 * 8;
-  if (h->mode == MODE_F32_I8) k_init_random<ModeF32I8><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi);
-  else if (h->mode == MODE_F32_F) k_init_random<ModeF32F><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi);
-  else k_init_random<ModeF64><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi);
+  if (h->mode == MODE_F32_I8) k_init_random<ModeF32I8><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
+  else if (h->mode == MODE_F32_F) k_init_random<ModeF32F><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
+  else k_init_random<ModeF64><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   h->launches += 1;

@@ -531,13 +531,21 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
   }
   const RepConst &rc = s_rc;
 
-  QT *Qp = reinterpret_cast<QT *>(a.Q) + (long long)rep * g.site_stride * 4;
+  const bool dq = (a.algo == 3);  // Double Q-learning keeps two tables per site: [site][table][s][a]
+  QT *Qp = reinterpret_cast<QT *>(a.Q) + (long long)rep * g.site_stride * (dq ? 8 : 4);
   const RT *R_in = reinterpret_cast<const RT *>(a.R_in) + (long long)rep * g.plane_stride;
   RT *R_out = reinterpret_cast<RT *>(a.R_out) + (long long)rep * g.plane_stride;
   const Code *code_in = reinterpret_cast<const Code *>(a.code_in) + (long long)rep * g.plane_stride;
   Code *code_out = reinterpret_cast<Code *>(a.code_out) + (long long)rep * g.plane_stride;
   const uint32_t *S_in = a.S_in + (long long)rep * g.bits_stride;
   uint32_t *S_out = a.S_out + (long long)rep * g.bits_stride;
+  // contraction-free arithmetic in the table's precision (reference operation order in fp64)
+  auto q_add = [](QT x, QT y) -> QT { if constexpr (Md::kFp64) return __dadd_rn(x, y); else return __fadd_rn(x, y); };
+  auto q_sub = [](QT x, QT y) -> QT { if constexpr (Md::kFp64) return __dsub_rn(x, y); else return __fsub_rn(x, y); };
+  auto q_mul = [](QT x, QT y) -> QT { if constexpr (Md::kFp64) return __dmul_rn(x, y); else return __fmul_rn(x, y); };
+  auto q_div = [](QT x, QT y) -> QT { if constexpr (Md::kFp64) return __ddiv_rn(x, y); else return __fdiv_rn(x, y); };
+  auto q_max = [](QT x, QT y) -> QT { return x > y ? x : (y > x ? y : x); };
+  auto q_mean = [&](QT x, QT y) -> QT { return q_div(q_add(x, y), QT(2)); };
 
   // scalars of this launch
   Val inv_den = Val(0), den = Val(1);
@@ -624,7 +632,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
         }
       }
       uint32_t wS1[4] = {0, 0, 0, 0}, wS2[4] = {0, 0, 0, 0};
-      if (upd && a.algo == 1 && a.u2 == nullptr) {
+      if (upd && (a.algo == 1 || a.algo == 3) && a.u2 == nullptr) {
         // SARSA's two further draws of iteration j: Philox streams 1 and 2 (counter word 3)
 #pragma unroll
         for (int st = 1; st <= 2; ++st) {
@@ -651,7 +659,13 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
         if (valid) {
           const long long site = (long long)i * g.L + col;
           QT q0_, q1_, q2_, q3_;
-          if constexpr (Md::kFp64) {
+          QT t1[4], t2[4];  // Double Q-learning: the two tables (algorithms.py:245-247); q*_ = their mean
+          if (dq) {
+#pragma unroll
+            for (int z = 0; z < 4; ++z) { t1[z] = Qp[site * 8 + z]; t2[z] = Qp[site * 8 + 4 + z]; }
+            q0_ = q_mean(t1[0], t2[0]); q1_ = q_mean(t1[1], t2[1]);   // get_combined_q_table, algorithms.py:263
+            q2_ = q_mean(t1[2], t2[2]); q3_ = q_mean(t1[3], t2[3]);
+          } else if constexpr (Md::kFp64) {
             const double2 lo2 = reinterpret_cast<const double2 *>(Qp)[site * 2];
             const double2 hi2 = reinterpret_cast<const double2 *>(Qp)[site * 2 + 1];
             q0_ = lo2.x; q1_ = lo2.y; q2_ = hi2.x; q3_ = hi2.y;
@@ -701,7 +715,57 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
                 ex2 = (wS2[k4] >> 8) < thr_u; rn2 = (int)(wS2[k4] & 1u);
               }
             }
-            if constexpr (Md::kFp64) {
+            bool dq_done = false;
+            if (dq) {
+              // Double Q-learning (algorithms.py:292-341): a fair draw picks the table to update;
+              // its TD target is the max of the OTHER table's row of s' (as the reference codes
+              // it: next_q_1 = Q2[s', argmax Q2[s']], :320-325)
+              const bool upd1 = (a.u2 != nullptr) ? (a.u2[site] < 0.5) : ((wS1[k4] >> 8) < (1u << 23));
+              const int r0i = 2 * s_new;
+              const QT nx1 = q_max(t2[r0i], t2[r0i + 1]), nx2 = q_max(t1[r0i], t1[r0i + 1]);
+              const QT g_ = Md::kFp64 ? (QT)rc.gamma : (QT)rc.gamma_f, al_ = Md::kFp64 ? (QT)rc.alpha : (QT)rc.alpha_f;
+              if (upd1) t1[e] = q_add(t1[e], q_mul(al_, q_sub(q_add(vx, q_mul(g_, nx1)), t1[e])));
+              else t2[e] = q_add(t2[e], q_mul(al_, q_sub(q_add(vx, q_mul(g_, nx2)), t2[e])));
+              // TD error of the combined table after the write (spgg.py:464-468)
+              QT cq[4];
+#pragma unroll
+              for (int z = 0; z < 4; ++z) cq[z] = q_mean(t1[z], t2[z]);
+              qtd = cq[e];
+              const QT td2 = q_sub(q_add(vx, q_mul(g_, q_max(cq[r0i], cq[r0i + 1]))), qtd);
+              QT lam;
+              if constexpr (Md::kFp64) lam = __ddiv_rn(__dmul_rn(rc.kappa, fmax(0.0, best)), den);
+              else lam = __fmul_rn(__fmul_rn(rc.kappa_f, fmaxf(0.0f, best)), inv_den);
+              const QT nu = same ? lam : -lam;
+              t1[e] = q_add(t1[e], nu);                      // spgg.py:499-505: both tables
+              t2[e] = q_add(t2[e], nu);
+              q0_ = q_mean(t1[0], t2[0]); q1_ = q_mean(t1[1], t2[1]);
+              q2_ = q_mean(t1[2], t2[2]); q3_ = q_mean(t1[3], t2[3]);
+              qfin = sel4<QT>(e, q0_, q1_, q2_, q3_);
+              const QT an = nu < QT(0) ? -nu : nu;
+              const QT atd = q_mul(al_, td2);
+              const QT pct = q_mul(q_div(an, q_add(q_add(atd < QT(0) ? -atd : atd, an), (QT)1e-8)), (QT)100.0);
+              if constexpr (Md::kFp64) {
+                sumNI += pct;
+                const double P = payoff_f64(code, rc);
+                sumP += P;
+                if (wasC) sumPC += P; else sumPD += P;
+                sumWP += __dmul_rn(rc.wP, P);
+                if (coop) {
+                  sumRewC += vx;
+                  sumRatio += __dmul_rn(
+                      __ddiv_rn(fabs(__dmul_rn(rc.wR, 0.5)), __dadd_rn(fabs(vx), 1e-9)), 100.0);
+                } else {
+                  sumRewD += vx;
+                }
+              } else {
+                tni += pct;
+                pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
+                if (rc.has_ratio && coop) tratio += sm_ratio[code >> 1];
+              }
+              dq_done = true;
+            }
+            if (dq_done) {
+            } else if constexpr (Md::kFp64) {
               // value of the next state: max (algorithms.py:125), Q[s'][a'] (:169) or the
               // eps-greedy expectation p0*Q[s'][0] + p1*Q[s'][1] (:212-224)
               auto next_value = [&](double x0, double x1, bool ex, int rn) -> double {
@@ -759,10 +823,12 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
               pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
               if (rc.has_ratio && coop) tratio += sm_ratio[code >> 1];
             }
-            q0_ = (e == 0) ? qfin : q0_;
-            q1_ = (e == 1) ? qfin : q1_;
-            q2_ = (e == 2) ? qfin : q2_;
-            q3_ = (e == 3) ? qfin : q3_;
+            if (!dq) {
+              q0_ = (e == 0) ? qfin : q0_;
+              q1_ = (e == 1) ? qfin : q1_;
+              q2_ = (e == 2) ? qfin : q2_;
+              q3_ = (e == 3) ? qfin : q3_;
+            }
             pk_n += 1u << (8 * (wasC * 2 + coop));
             if (best > Val(0)) { n_best += 1u; n_best2 += (kstar >= 4); }
             pk_grp += 1ull << (10 * (5 - (int)sm_N[sidx]));                              // spgg.py:586-592
@@ -810,7 +876,10 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
             store_cell<RT>(R_out, g, i, col, r_new);
           }
           if (upd) {
-            if constexpr (Md::kFp64) {
+            if (dq) {
+#pragma unroll
+              for (int z = 0; z < 4; ++z) { Qp[site * 8 + z] = t1[z]; Qp[site * 8 + 4 + z] = t2[z]; }
+            } else if constexpr (Md::kFp64) {
               reinterpret_cast<double2 *>(Qp)[site * 2] = make_double2(q0_, q1_);
               reinterpret_cast<double2 *>(Qp)[site * 2 + 1] = make_double2(q2_, q3_);
             } else {
@@ -988,23 +1057,25 @@ __global__ void k_halo_unpack(Geom g, void *code, void *R, uint32_t *S, const un
 // 2 (S) in word 3 so they never collide with the per-iteration draws (stream 0).
 template <class Md>
 __global__ void k_init_random(Geom g, int rep, void *Q, void *R, uint32_t *S, uint32_t seed_lo,
-                              uint32_t seed_hi) {
+                              uint32_t seed_hi, int nq) {
   typedef typename Md::Q QT;
   typedef typename Md::R RT;
-  QT *Qp = reinterpret_cast<QT *>(Q) + (long long)rep * g.site_stride * 4;
+  QT *Qp = reinterpret_cast<QT *>(Q) + (long long)rep * g.site_stride * nq;
   RT *Rp = reinterpret_cast<RT *>(R) + (long long)rep * g.plane_stride;
   uint32_t *Sp = S + (long long)rep * g.bits_stride;
   const long long n_sites = g.site_stride;
   for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n_sites;
        x += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(x / g.L), j = (int)(x % g.L);
-    uint32_t w[4];
-    philox4x32_10((uint32_t)j, (uint32_t)(g.row0 + i), 0u, 1u, seed_lo, seed_hi, w);
+    for (int t = 0; t < nq / 4; ++t) {  // one table, or the two of Double Q-learning
+      uint32_t w[4];
+      philox4x32_10((uint32_t)j, (uint32_t)(g.row0 + i), (uint32_t)t, 1u, seed_lo, seed_hi, w);
 #pragma unroll
-    for (int z = 0; z < 4; ++z) {
-      // 24-bit uniform in [0,1) -> [-0.01, 0.01)
-      const double uu = (double)(w[z] >> 8) * (1.0 / 16777216.0);
-      Qp[x * 4 + z] = (QT)(-0.01 + 0.02 * uu);
+      for (int z = 0; z < 4; ++z) {
+        // 24-bit uniform in [0,1) -> [-0.01, 0.01)
+        const double uu = (double)(w[z] >> 8) * (1.0 / 16777216.0);
+        Qp[x * nq + 4 * t + z] = (QT)(-0.01 + 0.02 * uu);
+      }
     }
   }
   // strategy bits from stream 2, written through the ghost-aware store; R planes are zero
@@ -1032,10 +1103,10 @@ __global__ void k_init_random(Geom g, int rep, void *Q, void *R, uint32_t *S, ui
 template <class Md>
 __global__ void k_import_rows(Geom g, int rep, int i0, int nrows, const uint8_t *S, const double *R,
                               const double *Q, void *Qd, void *Rd, uint32_t *Sd, double rq,
-                              unsigned long long *info) {
+                              unsigned long long *info, int nq) {
   typedef typename Md::Q QT;
   typedef typename Md::R RT;
-  QT *Qp = reinterpret_cast<QT *>(Qd) + (long long)rep * g.site_stride * 4;
+  QT *Qp = reinterpret_cast<QT *>(Qd) + (long long)rep * g.site_stride * nq;
   RT *Rp = reinterpret_cast<RT *>(Rd) + (long long)rep * g.plane_stride;
   uint32_t *Sp = Sd + (long long)rep * g.bits_stride;
   const int lane = threadIdx.x & 31;
@@ -1064,8 +1135,7 @@ __global__ void k_import_rows(Geom g, int rep, int i0, int nrows, const uint8_t 
         rv = (RT)r;
       }
       const long long site = (long long)i * g.L + col;
-#pragma unroll
-      for (int z = 0; z < 4; ++z) Qp[site * 4 + z] = (QT)Q[src * 4 + z];
+      for (int z = 0; z < nq; ++z) Qp[site * nq + z] = (QT)Q[src * nq + z];
     }
     const uint32_t word = __ballot_sync(0xffffffffu, valid && bit);
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
@@ -1078,10 +1148,10 @@ __global__ void k_import_rows(Geom g, int rep, int i0, int nrows, const uint8_t 
 
 template <class Md>
 __global__ void k_export_rows(Geom g, int rep, int i0, int nrows, uint8_t *S, double *R, double *Q,
-                              const void *Qd, const void *Rd, const uint32_t *Sd, double rq) {
+                              const void *Qd, const void *Rd, const uint32_t *Sd, double rq, int nq) {
   typedef typename Md::Q QT;
   typedef typename Md::R RT;
-  const QT *Qp = reinterpret_cast<const QT *>(Qd) + (long long)rep * g.site_stride * 4;
+  const QT *Qp = reinterpret_cast<const QT *>(Qd) + (long long)rep * g.site_stride * nq;
   const RT *Rp = reinterpret_cast<const RT *>(Rd) + (long long)rep * g.plane_stride;
   const uint32_t *Sp = Sd + (long long)rep * g.bits_stride;
   const long long n = (long long)nrows * g.L;
@@ -1096,8 +1166,7 @@ __global__ void k_export_rows(Geom g, int rep, int i0, int nrows, uint8_t *S, do
     }
     if (Q) {
       const long long site = (long long)i * g.L + col;
-#pragma unroll
-      for (int z = 0; z < 4; ++z) Q[e * 4 + z] = (double)Qp[site * 4 + z];
+      for (int z = 0; z < nq; ++z) Q[e * nq + z] = (double)Qp[site * nq + z];
     }
   }
 }

@@ -14,7 +14,8 @@ from . import _lib as L_
 
 _ALGOS = {"qlearning": L_.ALGO_QLEARNING, "q-learning": L_.ALGO_QLEARNING,
           "sarsa": L_.ALGO_SARSA,
-          "expected_sarsa": L_.ALGO_EXPECTED_SARSA, "expected-sarsa": L_.ALGO_EXPECTED_SARSA}
+          "expected_sarsa": L_.ALGO_EXPECTED_SARSA, "expected-sarsa": L_.ALGO_EXPECTED_SARSA,
+          "double_qlearning": L_.ALGO_DOUBLE_QLEARNING, "double-q-learning": L_.ALGO_DOUBLE_QLEARNING}
 
 
 def params_struct(p: dict, seed: int = 0, precision: str = "fp32", rows=None, row0: int = 0,
@@ -28,9 +29,6 @@ def params_struct(p: dict, seed: int = 0, precision: str = "fp32", rows=None, ro
                          f"Must be 'reputation' or 'action'")
     algo = str(p.get("algorithm", "qlearning")).lower()
     if algo not in _ALGOS:
-        if algo in ("double_qlearning", "double-q-learning"):
-            raise ValueError(f"algorithm '{algo}' is not built into the fused CUDA step yet "
-                             "(two Q tables); there is no CPU fallback")
         # same message as algorithms.py:382-383
         raise ValueError(f"Unknown algorithm: {algo}. "
                          f"Supported: 'qlearning', 'sarsa', 'expected_sarsa', 'double_qlearning'")
@@ -74,6 +72,8 @@ class Engine:
         self.L = int(arr[0].L)
         self.rows = int(arr[0].rows)
         self.precision = precision
+        # Q values per site: 4, or the two tables of Double Q-learning ([site][table][s][a])
+        self.nq = 8 if int(arr[0].algorithm) == L_.ALGO_DOUBLE_QLEARNING else 4
         self._h = C.c_void_p()
         L_.check(self.lib.spgg_create(arr, n, int(device), C.byref(self._h)))
         self.device = int(device)
@@ -97,8 +97,9 @@ class Engine:
         S8 = np.ascontiguousarray(np.asarray(S).reshape(-1) != 0, dtype=np.uint8)
         Rd = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(-1))
         Qd = np.ascontiguousarray(np.asarray(Q, dtype=np.float64).reshape(-1))
-        if S8.size != n or Rd.size != n or Qd.size != 4 * n:
-            raise ValueError(f"state arrays must describe {self.rows}x{self.L} sites")
+        if S8.size != n or Rd.size != n or Qd.size != self.nq * n:
+            raise ValueError(f"state arrays must describe {self.rows}x{self.L} sites "
+                             f"({self.nq} Q values per site)")
         L_.check(self.lib.spgg_set_state(self._h, replica, S8.ctypes.data, Rd.ctypes.data,
                                          Qd.ctypes.data))
 
@@ -109,13 +110,13 @@ class Engine:
         n = self.rows * self.L
         S = np.empty(n, np.uint8)
         R = np.empty(n, np.float64)
-        Q = np.empty(4 * n, np.float64) if want_q else None
+        Q = np.empty(self.nq * n, np.float64) if want_q else None
         L_.check(self.lib.spgg_get_state(self._h, replica, S.ctypes.data, R.ctypes.data,
                                          Q.ctypes.data if want_q else None))
         S = S.reshape(self.rows, self.L)
         R = R.reshape(self.rows, self.L)
         if want_q:
-            Q = Q.reshape(self.rows, self.L, 2, 2)
+            Q = Q.reshape((self.rows, self.L, 2, 2) if self.nq == 4 else (self.rows, self.L, 2, 2, 2))
         return S, R, Q
 
     def set_replay(self, u, b):

@@ -71,6 +71,9 @@ class SPGG:
             raise ValueError(f"algorithm must be str or RLAlgorithm, got {type(algorithm)}")
 
         self.q_table = rng.uniform(low=-0.01, high=0.01, size=(L, L, 2, 2))   # spgg.py:121
+        if hasattr(self.algorithm, "initialize_q_tables"):                    # spgg.py:124-127
+            self.algorithm.initialize_q_tables(self.q_table.shape, rng)
+            self.q_table = self.algorithm.get_combined_q_table()
         self.R = np.zeros((L, L))                                              # spgg.py:129
         self.cache = {}
         self._Sn = S_in_one
@@ -129,7 +132,7 @@ class SPGG:
         if getattr(self.algorithm, "kernel_tag", None) is None:
             raise ValueError(
                 f"algorithm '{getattr(self.algorithm, 'name', type(self.algorithm).__name__)}' is not "
-                "built into the fused CUDA step (Q-learning, SARSA and Expected SARSA are); "
+                "built into the fused CUDA step (the reference's four rules are); "
                 "there is no CPU fallback")
 
     def _snapshot(self, eng, i, data_file, snaps, replica=0):
@@ -187,10 +190,11 @@ def run_models(models, filenames):
     chunk_max = int(m0.params.get("chunk", 4096))
     for m in models[1:]:
         if (m.L, bool(m.use_second_order), m.state_representation, m.params.get("precision", "fp32"),
-                int(m.iterations)) != (L, bool(m0.use_second_order), m0.state_representation, precision,
-                                       int(m0.iterations)):
+                int(m.iterations), getattr(m.algorithm, "kernel_tag", None)) != (
+                L, bool(m0.use_second_order), m0.state_representation, precision,
+                int(m0.iterations), getattr(m0.algorithm, "kernel_tag", None)):
             raise ValueError("batched models must share L, use_second_order, state_representation, "
-                             "precision and iterations")
+                             "precision, iterations and algorithm")
     if draws == "numpy":
         if n != 1:
             raise ValueError("draws='numpy' (replay of the reference's stream) runs one model at a time")
@@ -207,7 +211,10 @@ def run_models(models, filenames):
     results = []
     try:
         for r, m in enumerate(models):
-            eng.set_state(m._Sn, m.R, m.q_table, replica=r)
+            q_host = m.q_table
+            if eng.nq == 8:   # Double Q-learning: both tables, [site][table][s][a]
+                q_host = np.stack([m.algorithm.q_table_1, m.algorithm.q_table_2], axis=2)
+            eng.set_state(m._Sn, m.R, q_host, replica=r)
         rows_it = [[] for _ in models]
         sum_r_before = [[] for _ in models]
         stop_sum_r = [0.0] * n
@@ -225,13 +232,15 @@ def run_models(models, filenames):
             if draws == "numpy":
                 # the reference's stream: per iteration rand(L,L) then randint(0,2,(L,L))
                 # (algorithms.py:105,108); SARSA draws three such pairs (spgg.py:410,433,452)
-                pairs = 3 if getattr(m0.algorithm, "kernel_tag", "") == "sarsa" else 1
+                tag = getattr(m0.algorithm, "kernel_tag", "")
+                pairs = {"sarsa": 3, "double_qlearning": 2}.get(tag, 1)
                 u = np.empty((k_req, pairs, L, L))
-                b = np.empty((k_req, pairs, L, L), np.uint8)
+                b = np.zeros((k_req, pairs, L, L), np.uint8)
                 for i in range(k_req):
                     for q in range(pairs):
                         u[i, q] = m0._rng.rand(L, L)
-                        b[i, q] = m0._rng.randint(0, 2, size=(L, L))
+                        if not (tag == "double_qlearning" and q == 1):  # Double-Q: rand, randint, rand
+                            b[i, q] = m0._rng.randint(0, 2, size=(L, L))
                 eng.set_replay(u if pairs > 1 else u[:, 0], b if pairs > 1 else b[:, 0])
             eng.step(k_req)
             for r, m in enumerate(models):
@@ -252,6 +261,10 @@ def run_models(models, filenames):
         launches = int(eng.status().kernel_launches)
         for r, m in enumerate(models):
             S, R, Q = eng.get_state(r)
+            if eng.nq == 8:
+                m.algorithm.q_table_1 = np.ascontiguousarray(Q[:, :, 0])
+                m.algorithm.q_table_2 = np.ascontiguousarray(Q[:, :, 1])
+                Q = m.algorithm.get_combined_q_table()
             ri = np.vstack(rows_it[r]) if rows_it[r] else np.zeros((0, L_.NSTAT))
             sb = np.concatenate(sum_r_before[r]) if sum_r_before[r] else np.zeros(0)
             ser = series.assemble(ri, sb, N, m.params, eps0[r], stopped=stopped[r],

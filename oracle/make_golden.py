@@ -94,24 +94,40 @@ TD_CASES = {
     "expsarsa_act_m1": dict(RUNNER_FIXED, L=14, iterations=30, r=4.0, influence_factor=1.0,
                             use_second_order=False, reward_weight_payoff=1.0, rep_gain_C=1.0,
                             state_representation="action", algorithm="expected_sarsa"),
+    "doubleq_rep_m1": dict(RUNNER_FIXED, L=12, iterations=30, r=3.0, influence_factor=1.0,
+                           use_second_order=False, reward_weight_payoff=0.95, rep_gain_C=1.0,
+                           state_representation="reputation", algorithm="double_qlearning"),
+    "doubleq_act_m2": dict(RUNNER_FIXED, L=12, iterations=30, r=4.0, influence_factor=1.0,
+                           use_second_order=True, reward_weight_payoff=1.0, rep_gain_C=1.0,
+                           state_representation="action", algorithm="double_qlearning"),
 }
 
 
 def make_replay(name, params, seed):
     out = ref_harness.run_reference(seed, **params)
+    extra = {}
     if "u" not in out:
-        # rules that draw more than one pair per iteration (SARSA: 3 pairs, spgg.py:410,433,452):
-        # keep the stream as (n_steps, pairs, L, L)
+        # rules that draw more than one pair per iteration: keep the stream as (n_steps, pairs, L, L).
+        # SARSA: 3 (rand, randint) pairs (spgg.py:410,433,452).  Double-Q: rand, randint, rand
+        # (algorithms.py:285,288,303) -> 2 "pairs", the second randint slot is zero padding.
         n, L = out["n_steps"], params["L"]
         pairs = len(out["rand"]) // max(n, 1)
-        assert pairs * n == len(out["rand"]) == len(out["randint"])
+        assert pairs * n == len(out["rand"])
         out["u"] = np.stack(out["rand"]).reshape(n, pairs, L, L)
-        out["b"] = np.stack(out["randint"]).astype(np.uint8).reshape(n, pairs, L, L)
+        if len(out["randint"]) == len(out["rand"]):
+            out["b"] = np.stack(out["randint"]).astype(np.uint8).reshape(n, pairs, L, L)
+        else:
+            assert pairs == 2 and len(out["randint"]) == n
+            out["b"] = np.zeros((n, 2, L, L), np.uint8)
+            out["b"][:, 0] = np.stack(out["randint"])
+        for k in ("q1_0", "q2_0", "q1_final", "q2_final"):
+            if k in out:
+                extra[k] = out[k]
     blob = dict(params_json=np.array(json.dumps(params)), seed=np.array(seed),
                 q0=out["q0"], s0=out["s0"].astype(np.uint8), u=out["u"], b=out["b"],
                 q_final=out["q_final"], r_final=out["r_final"],
                 s_final=out["s_final"].astype(np.uint8),
-                ret=np.array(out["ret"], dtype=np.float64))
+                ret=np.array(out["ret"], dtype=np.float64), **extra)
     for k in KEEP_DATASETS:
         if k in out["datasets"]:
             blob["ds_" + k] = out["datasets"][k]

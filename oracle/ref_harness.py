@@ -169,6 +169,9 @@ def run_reference(seed: int, cluster_tail: bool = True, **params):
     with pinned_seed(seed):
         model = ref_model.SPGG(**params)
     q0 = model.q_table.copy()
+    dq_tables0 = None
+    if getattr(model.algorithm, "q_table_1", None) is not None:   # DoubleQLearning (algorithms.py:245-260)
+        dq_tables0 = (model.algorithm.q_table_1.copy(), model.algorithm.q_table_2.copy())
     s0 = model._Sn.copy()
     r0 = model.R.copy()
     tmp = tempfile.mkdtemp(prefix="spgg_ref_")
@@ -194,6 +197,10 @@ def run_reference(seed: int, cluster_tail: bool = True, **params):
         "ret": ret,
         "n_steps": n_steps,
     }
+    if dq_tables0 is not None:
+        out["q1_0"], out["q2_0"] = dq_tables0
+        out["q1_final"] = model.algorithm.q_table_1.copy()
+        out["q2_final"] = model.algorithm.q_table_2.copy()
     if algo == "QLearning":
         # one rand + one randint per completed step (algorithms.py:105,108)
         assert len(log["rand"]) == n_steps and len(log["randint"]) == n_steps

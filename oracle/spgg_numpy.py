@@ -135,6 +135,11 @@ def qlearning_step(S, R, Q, eps, u, b, p, algo="qlearning", extra=None):
     st["rep_avg"] = np.mean(R)
     st["P"] = P
 
+    dq = (algo == "double_qlearning")
+    if dq:
+        # two tables; the policy and every statistic use their mean (algorithms.py:263, 283-290)
+        QA, QB = Q[0].copy(), Q[1].copy()
+        Q = (QA + QB) / 2
     s_old = state_of(R, S, M, p["state_representation"])          # spgg.py:409
     greedy = np.argmax(Q[ii, jj, s_old, :], axis=2)               # algorithms.py:106-107
     a = np.where(u < eps, b.astype(np.int64), greedy)             # algorithms.py:105,109
@@ -150,17 +155,32 @@ def qlearning_step(S, R, Q, eps, u, b, p, algo="qlearning", extra=None):
     st["rep_component"] = np.mean(wR * rep_reward)
     rew = wP * P + wR * rep_reward                                # spgg.py:427
 
-    Q2 = Q.copy()
-    q0 = Q[ii, jj, s_old, a]
-    x1 = extra[0] if extra else (None, None)
-    x2 = extra[1] if extra else (None, None)
-    nxt = _td_target(Q, ii, jj, s_new, algo, eps, *x1)
-    td = rew + gamma * nxt - q0                                   # algorithms.py:128
-    Q2[ii, jj, s_old, a] = q0 + alpha * td                        # algorithms.py:131
+    if dq:
+        # algorithms.py:292-341: rand(L,L) < 0.5 picks the table to update; its target is the
+        # other table's value at the other table's greedy action, i.e. that table's row maximum
+        upd1 = extra[0] < 0.5
+        qa, qb = QA[ii, jj, s_old, a], QB[ii, jj, s_old, a]
+        nxt_a = np.max(QB[ii, jj, s_new, :], axis=2)
+        nxt_b = np.max(QA[ii, jj, s_new, :], axis=2)
+        td_a = rew + gamma * nxt_a - qa
+        td_b = rew + gamma * nxt_b - qb
+        QA[ii[upd1], jj[upd1], s_old[upd1], a[upd1]] += alpha * td_a[upd1]
+        QB[ii[~upd1], jj[~upd1], s_old[~upd1], a[~upd1]] += alpha * td_b[~upd1]
+        Q2 = (QA + QB) / 2
+        q_cur = Q2[ii, jj, s_old, a]                              # spgg.py:464-468
+        td2 = rew + gamma * np.max(Q2[ii, jj, s_new, :], axis=2) - q_cur
+    else:
+        Q2 = Q.copy()
+        q0 = Q[ii, jj, s_old, a]
+        x1 = extra[0] if extra else (None, None)
+        x2 = extra[1] if extra else (None, None)
+        nxt = _td_target(Q, ii, jj, s_new, algo, eps, *x1)
+        td = rew + gamma * nxt - q0                               # algorithms.py:128
+        Q2[ii, jj, s_old, a] = q0 + alpha * td                    # algorithms.py:131
 
-    # TD error on the updated table, only feeds the NI statistic (spgg.py:446-473)
-    q_cur = Q2[ii, jj, s_old, a]
-    td2 = rew + gamma * _td_target(Q2, ii, jj, s_new, algo, eps, *x2) - q_cur
+        # TD error on the updated table, only feeds the NI statistic (spgg.py:446-473)
+        q_cur = Q2[ii, jj, s_old, a]
+        td2 = rew + gamma * _td_target(Q2, ii, jj, s_new, algo, eps, *x2) - q_cur
 
     diffs = np.stack([at(rew, di, dj) - rew for (di, dj) in offs])  # spgg.py:486
     best = diffs.max(axis=0)
@@ -170,7 +190,12 @@ def qlearning_step(S, R, Q, eps, u, b, p, algo="qlearning", extra=None):
     nbr_a = np.stack([at(a, di, dj) for (di, dj) in offs])
     a_star = nbr_a[kstar, ii, jj]
     nu = lam * np.where(a_star == a, 1.0, -1.0)                   # spgg.py:494-495
-    Q2[ii, jj, s_old, a] += nu                                    # spgg.py:509
+    if dq:                                                        # spgg.py:498-505
+        QA[ii, jj, s_old, a] += nu
+        QB[ii, jj, s_old, a] += nu
+        Q2 = (QA + QB) / 2
+    else:
+        Q2[ii, jj, s_old, a] += nu                                # spgg.py:509
     st["gmax"] = gmax
 
     pct = np.abs(nu) / (np.abs(alpha * td2) + np.abs(nu) + 1e-8) * 100
@@ -199,6 +224,8 @@ def qlearning_step(S, R, Q, eps, u, b, p, algo="qlearning", extra=None):
     for k in range(6):
         st[f"group_comp_d{k}"] = (int((nd == k).sum()) / (L * L)) * 100
     st["rew"] = rew
+    if dq:
+        return S2, R2, (QA, QB), st
     return S2, R2, Q2, st
 
 
@@ -207,7 +234,8 @@ def simulate(p, S0, R0, Q0, draws):
     series under the reference's HDF5 dataset names (spgg.py:595-629).
     ``draws(t, L)`` returns ``(u, b)`` for iteration ``t`` (1-based)."""
     L = S0.shape[0]
-    S, R, Q = S0.astype(np.int64).copy(), R0.astype(np.float64).copy(), Q0.copy()
+    S, R = S0.astype(np.int64).copy(), R0.astype(np.float64).copy()
+    Q = (Q0[0].copy(), Q0[1].copy()) if isinstance(Q0, tuple) else Q0.copy()   # Double-Q: (table 1, table 2)
     eps = p["epsilon"]
     series = {}
 
@@ -236,6 +264,9 @@ def simulate(p, S0, R0, Q0, draws):
         if algo == "sarsa":      # three draw pairs per iteration (spgg.py:410, 433, 452)
             u, b, u2, b2, u3, b3 = draws(t, L)
             S, R, Q, st = qlearning_step(S, R, Q, eps, u, b, p, algo, ((u2, b2), (u3, b3)))
+        elif algo == "double_qlearning":   # rand, randint, then rand for the table choice
+            u, b, u2 = draws(t, L)
+            S, R, Q, st = qlearning_step(S, R, Q, eps, u, b, p, algo, (u2,))
         else:
             u, b = draws(t, L)
             S, R, Q, st = qlearning_step(S, R, Q, eps, u, b, p, algo)
@@ -261,6 +292,9 @@ def simulate(p, S0, R0, Q0, draws):
             push(f"cooperators_{nm}_history", st["cooperators_" + nm])
             push(f"defectors_{nm}_history", st["defectors_" + nm])
     out = {k: np.array(v) for k, v in series.items()}
+    if isinstance(Q, tuple):
+        out["q1_final"], out["q2_final"] = Q
+        Q = (Q[0] + Q[1]) / 2
     out["Sn_final"], out["R_final"], out["q_final"] = S, R, Q
     out["snapshots"] = snaps
     out["P_last"] = P_last

@@ -92,8 +92,6 @@ def test_argument_validation_does_not_need_a_gpu():
         spgg_b200.Engine(dict(L=32, state_representation="nonsense"))
     with pytest.raises(ValueError):
         spgg_b200.Engine(dict(L=32, algorithm="bogus"))
-    with pytest.raises(ValueError, match="no CPU fallback"):
-        spgg_b200.Engine(dict(L=32, algorithm="double_qlearning"))
     with pytest.raises(ValueError):
         spgg_b200.Engine(dict(L=2))
     with pytest.raises(ValueError):

@@ -108,11 +108,42 @@ def test_philox_stream_stays_in_the_reference_seed_band(golden_dir, cfg):
         eng.close()
 
 
-def test_unbuilt_td_rule_fails_loudly(tmp_path):
+def test_foreign_algorithm_subclass_fails_loudly(tmp_path):
+    """The reference accepts any RLAlgorithm instance (spgg.py:115-116); a rule that is not one of
+    its four cannot run inside the fused kernel and must say so (no CPU fallback)."""
     import spgg_b200
-    m = spgg_b200.SPGG(L=16, iterations=3, algorithm="double_qlearning", seed=1)
+
+    class MyRule(spgg_b200.RLAlgorithm):
+        name = "my_rule"
+
+    m = spgg_b200.SPGG(L=16, iterations=3, algorithm=MyRule(0.1, 0.9, 0.5, 0.99, 0.01), seed=1)
     with pytest.raises(ValueError, match="no CPU fallback"):
         m.run(str(tmp_path / "x.h5"))
+
+
+@pytest.mark.parametrize("name", ["doubleq_rep_m1", "doubleq_act_m2"])
+def test_double_q_replays_the_reference(tmp_path, golden_dir, name):
+    """algorithms.py:237-341 + spgg.py:464-468,498-505: both tables, the combined table, S and R
+    bit for bit with the reference's own stream (rand, randint, rand per iteration)."""
+    import spgg_b200
+    z, p = load_golden(golden_dir, name)
+    m = spgg_b200.SPGG(**p, seed=int(z["seed"]), precision="fp64", draws="numpy")
+    assert np.array_equal(m.algorithm.q_table_1, z["q1_0"]) and np.array_equal(m.algorithm.q_table_2, z["q2_0"])
+    assert np.array_equal(m.q_table, z["q0"]) and np.array_equal(m._Sn, z["s0"])
+    m.folder = str(tmp_path)
+    ret = m.run(str(tmp_path / "run.h5"))
+    assert np.array_equal(m._Sn, z["s_final"]) and np.array_equal(m.R, z["r_final"])
+    assert np.array_equal(m.algorithm.q_table_1, z["q1_final"])
+    assert np.array_equal(m.algorithm.q_table_2, z["q2_final"])
+    assert np.array_equal(m.q_table, z["q_final"])
+    np.testing.assert_allclose(ret, z["ret"], rtol=1e-12)
+    got = _read(str(tmp_path / "run.h5"))
+    for k in [f[3:] for f in z.files if f.startswith("ds_")]:
+        want = z["ds_" + k]
+        if want.dtype.kind == "i":
+            assert np.array_equal(got[k], want), k
+        else:
+            np.testing.assert_allclose(got[k], want, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
 
 
 TD_GOLDEN = ["sarsa_rep_m1", "sarsa_act_m2", "expsarsa_rep_m2", "expsarsa_act_m1"]
@@ -172,7 +203,7 @@ def test_td_rules_engine_vs_numpy_oracle(algo):
         eng.close()
 
 
-@pytest.mark.parametrize("algo", ["sarsa", "expected_sarsa"])
+@pytest.mark.parametrize("algo", ["sarsa", "expected_sarsa", "double_qlearning"])
 def test_td_rules_throughput_mode_runs_and_is_reproducible(tmp_path, algo):
     """fp32 + Philox (streams 0/1/2 for SARSA) through the class: same seed -> same files."""
     import spgg_b200

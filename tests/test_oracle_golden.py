@@ -241,3 +241,23 @@ def test_numpy_oracle_other_td_rules_reproduce_reference(golden_dir, name):
     for key in ("coop_rate_history", "switch_C_to_D", "neighbor_influence_percent",
                 "avg_q_s0_c_history", "cooperators_q_s0_d_history"):
         assert np.array_equal(out[key], z["ds_" + key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("name", ["doubleq_rep_m1", "doubleq_act_m2"])
+def test_numpy_oracle_double_q_reproduces_reference(golden_dir, name):
+    """Double Q-learning (algorithms.py:237-341; two tables, table choice drawn per site,
+    neighbour term added to both, spgg.py:498-505) against the executed reference."""
+    from oracle import spgg_numpy
+    z, p = load_golden(golden_dir, name)
+    p = full_params(p)
+    L, n = p["L"], int(z["u"].shape[0])
+    u, b = z["u"], z["b"]
+    assert np.array_equal(z["q0"], (z["q1_0"] + z["q2_0"]) / 2)
+    out = spgg_numpy.simulate(dict(p, iterations=n), z["s0"].astype(np.int64), np.zeros((L, L)),
+                              (z["q1_0"], z["q2_0"]), lambda t, L_: (u[t - 1, 0], b[t - 1, 0], u[t - 1, 1]))
+    assert np.array_equal(out["Sn_final"], z["s_final"])
+    assert np.array_equal(out["R_final"], z["r_final"])
+    assert np.array_equal(out["q1_final"], z["q1_final"]) and np.array_equal(out["q2_final"], z["q2_final"])
+    assert np.array_equal(out["q_final"], z["q_final"])
+    for key in ("coop_rate_history", "switch_C_to_D", "neighbor_influence_percent", "avg_q_s0_c_history"):
+        assert np.array_equal(out[key], z["ds_" + key], equal_nan=True), key

@@ -104,3 +104,15 @@ def test_runner_folder_name_equals_reference():
     for args in [(3.0, 1.0, False, 0.8, 0.95, 1.0), (3.6, 0.0, True, 0.1, 1.0, 0.5, "action"),
                  (5, 2, True, 0.8, 0.9, 0.25, "reputation", "double_qlearning")]:
         assert runner.get_folder_name(*args) == ref_runner.get_folder_name(*args)
+
+
+def test_double_q_ctor_draw_order_equals_reference():
+    """spgg.py:121-127: uniform q_table (discarded), then table 1, table 2, then randint S."""
+    import spgg_b200
+    ref_model = ref_harness.import_reference()
+    with ref_harness.pinned_seed(9):
+        a = ref_model.SPGG(L=10, iterations=3, algorithm="double_qlearning")
+    b = spgg_b200.SPGG(L=10, iterations=3, algorithm="double_qlearning", seed=9)
+    assert np.array_equal(a.algorithm.q_table_1, b.algorithm.q_table_1)
+    assert np.array_equal(a.algorithm.q_table_2, b.algorithm.q_table_2)
+    assert np.array_equal(a.q_table, b.q_table) and np.array_equal(a._Sn, b._Sn)
