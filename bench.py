@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-L", type=int, default=4096)
+    ap.add_argument("--workload", default="c4", choices=["c4", "sweep"],
+                    help="c4: the headline L=4096 lattice (default); sweep: BASELINE config 3, the "
+                         "r x kappa x M grid as 60 batched L=200 replicas (not a driver bench line)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -195,6 +198,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if args.workload == "sweep":
+        return bench_sweep(args)
     dev = 0
     torch.cuda.set_device(dev)
     L = args.L or 4096
@@ -317,6 +322,49 @@ def main():
     }
     print(json.dumps(line), flush=True)
     eng.close()
+
+
+def bench_sweep(args):
+    """BASELINE config 3 on one GPU: r in {1,2,3,3.6,4,5} x kappa in {0,.5,1,1.5,2} x M in {1,2},
+    w_P=1, L=200 (the reference's figure_2_3_4 set is a subset) as two batches of 30 replicas.
+    Small lattices are L2-resident and launch/latency-bound; reported for completeness."""
+    import torch
+    import spgg_b200
+    L, inner = args.L or 200, args.inner
+    plist = [dict(C4, L=L, r=r, influence_factor=k, use_second_order=m, reward_weight_payoff=1.0)
+             for m in (False, True) for r in (1, 2, 3, 3.6, 4, 5) for k in (0, 0.5, 1, 1.5, 2)]
+    engines = []
+    for m in (False, True):
+        ps = [p for p in plist if p["use_second_order"] == m]
+        eng = spgg_b200.Engine(ps, seeds=list(range(len(ps))), precision="fp32")
+        for r in range(len(ps)):
+            eng.init_random(100 + r, replica=r)
+        engines.append(eng)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(args.warmup):
+        for eng in engines:
+            eng.step(inner, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        for eng in engines:
+            eng.step(inner, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    for eng in engines:
+        eng.sync()
+    value = len(plist) * L * L * inner * args.steps / (ms * 1e-3)
+    print(json.dumps({"metric": "site-updates/s", "value": value, "unit": "site-updates/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic",
+                      "config": {"workload": f"C3: {len(plist)} replicas L={L} (r x kappa x M grid), two batched "
+                                             f"handles, {inner} iterations per bench step, general kernel"}}),
+          flush=True)
+    for eng in engines:
+        eng.close()
 
 
 def state_bytes_dev(L):
