@@ -252,7 +252,7 @@ static int make_map_q(CUtensorMap *map, void *base, uint64_t L, uint64_t n_rows,
   }
   const cuuint64_t dims[4] = {128, L / 8, n_rows, n_rep};
   const cuuint64_t strides[3] = {128, L * 16, n_rows * L * 16};
-  const cuuint32_t box[4] = {128, TC / 8, 1, 1};
+  const cuuint32_t box[4] = {128, TC / 8, (cuuint32_t)FastSmem<1>::kRowsPerWarp, 1};  // a warp's rows of a tile
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

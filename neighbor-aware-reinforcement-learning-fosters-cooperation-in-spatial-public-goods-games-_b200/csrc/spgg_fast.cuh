@@ -56,10 +56,11 @@ struct FastSmem {
   static constexpr int kOffFlag = kOffBar + 40 * 8;            // "last CTA" flag
   static constexpr int kOffRc = kOffFlag + 16;                 // RepConst copy
   static constexpr int kOffRed = (kOffRc + (int)sizeof(RepConst) + 127) / 128 * 128;  // final reduction [8][NSTAT]
-  // per warp: kQBufs row segments of 128 float4 (2 KB each), landed by TMA with the 128-byte
-  // swizzle (1024-byte aligned) and written back in place
-  static constexpr int kQBufs = 4;
-  static constexpr int kQBufBytes = TC * 16;
+  // per warp: kQBufs buffers of kRowsPerWarp row segments of 128 float4 (2 KB each), landed by one
+  // TMA tile load with the 128-byte swizzle (1024-byte aligned) and written back in place
+  static constexpr int kRowsPerWarp = FTR / (FTHREADS / 32);
+  static constexpr int kQBufs = 2;
+  static constexpr int kQBufBytes = kRowsPerWarp * TC * 16;
   static constexpr int kOffQ = (kOffRed + 8 * NSTAT * 8 + 1023) / 1024 * 1024;
   static constexpr int kTotal = kOffQ + (FTHREADS / 32) * kQBufs * kQBufBytes + 1024;  // + base alignment slack
 };
@@ -270,13 +271,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     qoff[k] = (lane >> 1) * 128 + ((((lane & 1) * 4 + k) ^ ((lane >> 1) & 7)) << 4);
-  static_assert(FTR == 2 * (FTHREADS / 32), "the Q pipeline assumes two row segments per warp and tile");
-  int qb = 0;          // buffer holding the row segment this warp consumes next
-  uint32_t qph = 0;    // bit b: parity the next wait on buffer b expects
-  if (lane == 0 && cta < n_tiles) {  // both row segments of the first tile
-    q_issue((tx * TC) >> 3, ty * FTR + warp, 0);
-    q_issue((tx * TC) >> 3, ty * FTR + warp + FTHREADS / 32, 1);
-  }
+  // a warp owns kRowsPerWarp adjacent rows of every tile: one load, one store, one wait per tile
+  if (lane == 0 && cta < n_tiles) q_issue((tx * TC) >> 3, ty * FTR + warp * SM::kRowsPerWarp, 0);
 
   int tiles_done = 0, stage = 0;
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
@@ -358,19 +354,18 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     // ---- main phase: warp = one 128-site row segment, lane = 4 consecutive sites, so every
     // byte plane is read one 32-bit word and every reward row one float4 per lane
     const uint8_t *bCode = reinterpret_cast<const uint8_t *>(st_code);
+    // fetch this warp's rows of the CTA's next tile into the other buffer (its previous content,
+    // the rows of the previous tile, left by a tile store issued a whole tile ago)
+    const int qb = stage;
+    __syncwarp();
+    if (lane == 0) {
+      if (upd) tma_store_wait_read_n<0>();
+      if (has_next) q_issue((ntx * TC) >> 3, nty * FTR + warp * SM::kRowsPerWarp, qb ^ 1);
+    }
+    mbar_wait(&qbar[qb], (uint32_t)(tiles_done >> 1) & 1u);
 #pragma unroll 1
-    for (int rr = warp; rr < FTR; rr += FTHREADS / 32) {
-      // fetch the row segment two ahead (the same row of this CTA's next tile) into the buffer
-      // that held the segment two back
-      {
-        int nb = qb + 2;
-        if (nb >= SM::kQBufs) nb -= SM::kQBufs;
-        __syncwarp();  // every lane is done with the segment that last used buffer nb
-        if (lane == 0) {
-          if (upd) tma_store_wait_read_n<1>();  // ... and its tile store has left shared memory
-          if (has_next) q_issue((ntx * TC) >> 3, nty * FTR + rr, nb);
-        }
-      }
+    for (int r2 = 0; r2 < SM::kRowsPerWarp; ++r2) {
+      const int rr = warp * SM::kRowsPerWarp + r2;
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel) {
         // counter = (column / 4, global row, iteration, 0); one call -> this lane's 4 sites
@@ -444,9 +439,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           vl[0] = 0.f; vl[1] = sm_val[vb - 1]; vr[0] = sm_val[vb + 4]; vr[1] = 0.f;
         }
       }
-      unsigned char *qbuf = sQ + qb * SM::kQBufBytes;
-      mbar_wait(&qbar[qb], (qph >> qb) & 1u);
-      qph ^= 1u << qb;
+      unsigned char *qbuf = sQ + qb * SM::kQBufBytes + r2 * (TC * 16);
       // The four Q entries of a site stay in the landed segment: the entry being updated and
       // the row of the next state are addressed there (load/store pipe) instead of being
       // selected in registers - the integer/select pipe is the busy one in this loop.
@@ -456,6 +449,10 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       float qfin[4];
       int eidx[4];
       const uint32_t rowoffW = StW << 3;  // byte offset of row s' inside a site's 16 bytes, 4 sites
+      // per byte: the TD write lands in the row of s' (s' == s) and it is the C / the D entry
+      const uint32_t coopCW = (codeW >> 1) & 0x01010101u;
+      const uint32_t hitW = ~(StW ^ codeW) & 0x01010101u;
+      const uint32_t hitCW = hitW & coopCW, hitDW = hitW ^ hitCW;
       if (upd) {
         float qe[4], na[4], nb_[4];
         // byte offset of Q[s][a] (a = !coop) inside a site's 16 bytes: 4 * (2 s + a), 4 sites at once
@@ -471,8 +468,6 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t code = (codeW >> (8 * k)) & 0xFFu;
-          const int s = code & 1u, coop = (code >> 1) & 1u;
-          const int s_new = (StW >> (8 * k)) & 1u;
           const float vx = vc[k];
           // neighbour-aware term inputs: spgg.py:486-494, offsets in the order of spgg.py:479-485
           // ((dx,dy) names the site (i-dx, j-dy)); the first arg-max wins
@@ -500,15 +495,14 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
             const float d = __fsub_rn(nv[q], vx);
             if (d > best) { best = d; boff = no[q]; second = (q >= 4); }
           }
-          const bool same = (((bCode[vb + k + boff] >> 1) & 1u) == (unsigned)coop);
+          const bool same = ((((uint32_t)bCode[vb + k + boff] ^ code) >> 1) & 1u) == 0u;   // a* == a
           const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na[k], nb_[k]), vx), qe[k]);  // algorithms.py:128
           const float qtd = __fmaf_rn(alpha, td, qe[k]);                                   // algorithms.py:131
           const float lam = __fmul_rn(__fmul_rn(kappa, fmaxf(0.0f, best)), inv_den);       // spgg.py:489
           const float nu = same ? lam : -lam;                                              // spgg.py:494-495
           // TD error on the table after the TD write (spgg.py:446-473), for the NI statistic
-          const bool hit = (s_new == s);
-          const float na2 = (hit && coop) ? qtd : na[k];
-          const float nb2 = (hit && !coop) ? qtd : nb_[k];
+          const float na2 = ((hitCW >> (8 * k)) & 1u) ? qtd : na[k];
+          const float nb2 = ((hitDW >> (8 * k)) & 1u) ? qtd : nb_[k];
           const float td2 = __fsub_rn(__fmaf_rn(gamma, fmaxf(na2, nb2), vx), qtd);
           qfin[k] = __fadd_rn(qtd, nu);                                                    // spgg.py:509
           const float an = fabsf(nu);
@@ -572,15 +566,14 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           n_sel += __popc(coopbits);  // cooperating actions just chosen
         }
       }
-      if (upd) {
-        fence_proxy_async();  // the updated segment becomes visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d_hint(&tm.q, qbuf, 0, c0 >> 3, r0 + rr, rep, pol);
-          tma_store_commit();
-        }
+    }
+    if (upd) {
+      fence_proxy_async();  // the updated rows become visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d_hint(&tm.q, sQ + qb * SM::kQBufBytes, 0, c0 >> 3, r0 + warp * SM::kRowsPerWarp, rep, pol);
+        tma_store_commit();
       }
-      if (++qb == SM::kQBufs) qb = 0;
     }
     if (sel) fence_proxy_async();  // make out_* visible to the TMA engine
     __syncthreads();               // everyone is done with this stage, the work planes and out_*
