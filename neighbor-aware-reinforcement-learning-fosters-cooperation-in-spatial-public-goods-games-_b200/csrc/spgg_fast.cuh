@@ -363,7 +363,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       if (has_next) q_issue((ntx * TC) >> 3, nty * FTR + warp * SM::kRowsPerWarp, qb ^ 1);
     }
     mbar_wait(&qbar[qb], (uint32_t)(tiles_done >> 1) & 1u);
-#pragma unroll 1
+#pragma unroll
     for (int r2 = 0; r2 < SM::kRowsPerWarp; ++r2) {
       const int rr = warp * SM::kRowsPerWarp + r2;
       uint32_t w4[4] = {0, 0, 0, 0};

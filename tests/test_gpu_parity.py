@@ -238,6 +238,33 @@ def test_batched_replicas_equal_single_runs():
     eng.close()
 
 
+def test_batched_replicas_on_the_fast_path_equal_single_runs():
+    """Same as above on 128-aligned lattices (TMA fast path, grid = replicas x CTAs, per-replica
+    reward tables, Philox keys and early-exit flags)."""
+    L, n = 256, 40
+    plist = [full_params(dict(C1, L=L, r=r, influence_factor=k, reward_weight_payoff=w))
+             for r, k, w in ((3.0, 1.0, 0.95), (4.0, 0.0, 1.0), (5.0, 2.0, 0.9))]
+    rs = np.random.RandomState(5)
+    init = [(rs.randint(0, 2, (L, L)), rs.uniform(-0.01, 0.01, (L, L, 2, 2))) for _ in plist]
+    eng = _engine(plist, seeds=[20, 21, 22], precision="fp32")
+    for i, (S0, Q0) in enumerate(init):
+        eng.set_state(S0, np.zeros((L, L)), Q0, replica=i)
+    eng.step(n)
+    for i, (S0, Q0) in enumerate(init):
+        single = _engine(plist[i], seeds=20 + i, precision="fp32")
+        single.set_state(S0, np.zeros((L, L)), Q0)
+        single.step(n)
+        for a, b in zip(eng.get_state(i), single.get_state()):
+            assert np.array_equal(a, b)
+        ra, rb = eng.stats(i), single.stats()
+        exact = [c for c in range(18) if c != 10] + [31, 32, 33]
+        assert np.array_equal(ra[:, exact], rb[:, exact])
+        # the per-CTA partial sums are grouped differently when the grid is shared
+        np.testing.assert_allclose(ra[:, 18:31], rb[:, 18:31], rtol=1e-5, atol=1e-4)
+        single.close()
+    eng.close()
+
+
 def test_early_exit_matches_reference_semantics():
     """spgg.py:405: the loop breaks before acting once the lattice is uniform."""
     from oracle import spgg_numpy
