@@ -773,8 +773,8 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
     mbar_expect_tx(&bars[st], SM::kRowsCR * FROWB);
     tma_load_3d(stg + st * SM::kStageBytes, &ld_code, &bars[st], c0, r0 + GH - M, rep);
   };
-  float lmax = 0.f;
-  auto upd = [&](float x, float y) { lmax = fmaxf(lmax, fabsf(__fsub_rn(x, y))); };
+  float lmax4[4] = {0.f, 0.f, 0.f, 0.f};  // one running maximum per site of the lane: short dependency chains
+  auto upd = [&](int k, float x, float y) { lmax4[k] = fmaxf(lmax4[k], fabsf(__fsub_rn(x, y))); };
   int done = 0, stage = 0;
   for (int tile = gw; tile < n_tiles; tile += n_gw, ++done, stage ^= 1) {
     __syncwarp();  // every lane has left the stage about to be refilled
@@ -783,7 +783,7 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(stg + stage * SM::kStageBytes) + (CPAD / 4);
     float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f};  // rewards one / two rows up
     float u1l = 0.f, u1r = 0.f;                                        // ... and their row-neighbours
-#pragma unroll 2
+#pragma unroll 3
     for (int s = 0; s < FTR + M; ++s) {  // staged row s = tile row s - M
       const uint32_t w = cw[s * FROWW + lane];
       const uint32_t wl = cw[s * FROWW - 1];         // columns -4..-1 (same word for every lane)
@@ -806,13 +806,13 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
       if (s >= M) {  // a row of the tile: pairs with the rows above and to the left
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          upd(u1[k], c[k]);                                   // (1,0)
-          upd(k == 0 ? l1 : c[(k + 3) & 3], c[k]);            // (0,1)
+          upd(k, u1[k], c[k]);                                   // (1,0)
+          upd(k, k == 0 ? l1 : c[(k + 3) & 3], c[k]);            // (0,1)
           if constexpr (M == 2) {
-            upd(u2[k], c[k]);                                 // (2,0)
-            upd(k == 0 ? l2 : (k == 1 ? l1 : c[(k + 2) & 3]), c[k]);   // (0,2)
-            upd(k == 0 ? u1l : u1[(k + 3) & 3], c[k]);        // (1,1)
-            upd(k == 3 ? u1r : u1[(k + 1) & 3], c[k]);        // (1,-1)
+            upd(k, u2[k], c[k]);                                 // (2,0)
+            upd(k, k == 0 ? l2 : (k == 1 ? l1 : c[(k + 2) & 3]), c[k]);   // (0,2)
+            upd(k, k == 0 ? u1l : u1[(k + 3) & 3], c[k]);        // (1,1)
+            upd(k, k == 3 ? u1r : u1[(k + 1) & 3], c[k]);        // (1,-1)
           }
         }
       }
@@ -821,6 +821,7 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
       u1l = l1; u1r = r1;
     }
   }
+  float lmax = fmaxf(fmaxf(lmax4[0], lmax4[1]), fmaxf(lmax4[2], lmax4[3]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_down_sync(0xffffffffu, lmax, o));
   if (lane == 0) s_wmax[warp] = lmax;
