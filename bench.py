@@ -176,9 +176,10 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-L", type=int, default=4096)
-    ap.add_argument("--workload", default="c4", choices=["c4", "sweep"],
+    ap.add_argument("--workload", default="c4", choices=["c4", "sweep", "c1", "c2"],
                     help="c4: the headline L=4096 lattice (default); sweep: BASELINE config 3, the "
-                         "r x kappa x M grid as 60 batched L=200 replicas (not a driver bench line)")
+                         "r x kappa x M grid as 60 batched L=200 replicas; c1 / c2: the single small "
+                         "lattices of configs 0-2 (none of these is a driver bench line)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -198,7 +199,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    if args.workload == "sweep":
+    if args.workload != "c4":
         return bench_sweep(args)
     dev = 0
     torch.cuda.set_device(dev)
@@ -325,17 +326,35 @@ def main():
 
 
 def bench_sweep(args):
-    """BASELINE config 3 on one GPU: r in {1,2,3,3.6,4,5} x kappa in {0,.5,1,1.5,2} x M in {1,2},
-    w_P=1, L=200 (the reference's figure_2_3_4 set is a subset) as two batches of 30 replicas.
-    Small lattices are L2-resident and launch/latency-bound; reported for completeness."""
+    """Small-lattice workloads on one GPU (not the driver's bench line; BASELINE configs 0-3):
+      sweep  C3: r in {1,2,3,3.6,4,5} x kappa in {0,.5,1,1.5,2} x M in {1,2}, w_P=1, L=200 (the
+             reference's figure_2_3_4 set is a subset) as two batched handles of 30 replicas;
+      c1     the default_config.yaml run: one L=100 lattice, reputation state, M=1, r=3;
+      c2     one L=200 lattice, action state, M=2, r=4.
+    These lattices live in shared memory for a whole chunk (csrc/spgg_resident.cuh: one
+    thread-block cluster per replica); SPGG_NO_RESIDENT=1 times the per-iteration kernels."""
     import torch
     import spgg_b200
-    L, inner = args.L or 200, args.inner
-    plist = [dict(C4, L=L, r=r, influence_factor=k, use_second_order=m, reward_weight_payoff=1.0)
-             for m in (False, True) for r in (1, 2, 3, 3.6, 4, 5) for k in (0, 0.5, 1, 1.5, 2)]
+    inner = args.inner
+    if args.workload == "sweep":
+        L = args.L or 200
+        plist = [dict(C4, L=L, r=r, influence_factor=k, use_second_order=m, reward_weight_payoff=1.0)
+                 for m in (False, True) for r in (1, 2, 3, 3.6, 4, 5) for k in (0, 0.5, 1, 1.5, 2)]
+        what = f"C3: {len(plist)} replicas L={L} (r x kappa x M grid), two batched handles"
+    elif args.workload == "c1":
+        L = args.L or 100
+        plist = [dict(C4, L=L)]
+        what = f"C1: one lattice L={L}, reputation state, M=1, r=3, kappa=1, w_P=0.95"
+    else:
+        L = args.L or 200
+        plist = [dict(C4, L=L, r=4.0, use_second_order=True, reward_weight_payoff=1.0,
+                      state_representation="action")]
+        what = f"C2: one lattice L={L}, action state, M=2, r=4, kappa=1"
     engines = []
     for m in (False, True):
         ps = [p for p in plist if p["use_second_order"] == m]
+        if not ps:
+            continue
         eng = spgg_b200.Engine(ps, seeds=list(range(len(ps))), precision="fp32")
         for r in range(len(ps)):
             eng.init_random(100 + r, replica=r)
@@ -345,6 +364,7 @@ def bench_sweep(args):
         for eng in engines:
             eng.step(inner, stream)
     torch.cuda.synchronize()
+    l0 = sum(eng.status().kernel_launches for eng in engines)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -355,13 +375,24 @@ def bench_sweep(args):
     ms = e0.elapsed_time(e1)
     for eng in engines:
         eng.sync()
+    launches = sum(eng.status().kernel_launches for eng in engines) - l0
     value = len(plist) * L * L * inner * args.steps / (ms * 1e-3)
+    resident = launches <= len(engines) * args.steps
+    peak, peak_src = measured_peak_gbs()
     print(json.dumps({"metric": "site-updates/s", "value": value, "unit": "site-updates/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic",
-                      "config": {"workload": f"C3: {len(plist)} replicas L={L} (r x kappa x M grid), two batched "
-                                             f"handles, {inner} iterations per bench step, general kernel"}}),
+                      "data": "synthetic", "gpu_launches": int(launches),
+                      "us_per_iteration": 1e3 * ms / (args.steps * inner),
+                      "config": {"workload": f"{what}, {inner} iterations per bench step, "
+                                             + ("lattice-resident cluster kernel (state in shared memory, no HBM "
+                                                "traffic inside a chunk: latency/issue-bound, not HBM-bound)"
+                                                if resident else "per-iteration kernels (L2-resident, launch-bound)")},
+                      "roofline": {"bound": "hbm", "achieved": BYTES_PER_SITE_FP32 * value / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": BYTES_PER_SITE_FP32 * value / 1e9 / peak,
+                                   "traffic": None, "peak_source": peak_src,
+                                   "note": "same 34.25 B/site formula as C4 for comparison only; the state never "
+                                           "leaves the chip between iterations"}}),
           flush=True)
     for eng in engines:
         eng.close()

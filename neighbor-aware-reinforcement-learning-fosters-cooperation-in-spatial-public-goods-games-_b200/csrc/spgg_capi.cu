@@ -4,6 +4,7 @@
 #include "../../include/spgg.h"
 #include "spgg_kernels.cuh"
 #include "spgg_fast.cuh"
+#include "spgg_resident.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -76,6 +77,11 @@ struct spgg_handle {
   // fast path (spgg_fast.cuh): TMA descriptors of the two plane sets
   bool fast = false;
   FastMaps fmaps[2];  // [cur]: loads from plane set cur, stores into cur^1
+  // lattice-resident path (spgg_resident.cuh): one cluster per replica, whole chunks per launch
+  bool resident = false;
+  ResGeom rgeo{};
+  size_t smem_res = 0;
+  bool pend_resident = false;
   std::vector<double> eps_host;
   std::vector<uint32_t> thr_host;
   int replay_pairs = 1;
@@ -217,6 +223,26 @@ typedef void (*gfast_fn_t)(const CUtensorMap, GArgs);
 static gfast_fn_t pick_gfast(int M) { return M == 2 ? k_gmax_fast<2> : k_gmax_fast<1>; }
 static size_t gfast_smem(int M) { return M == 2 ? GmaxSmem<2>::kTotal : GmaxSmem<1>::kTotal; }
 
+// ---------------------------------------------------------------- resident path plumbing
+typedef void (*res_fn_t)(RArgs);
+static res_fn_t pick_res(int M, int action) {
+  if (M == 2) return action ? k_resident<2, true> : k_resident<2, false>;
+  return action ? k_resident<1, true> : k_resident<1, false>;
+}
+// geometry of the cluster decomposition, or CS = 0 when the lattice does not fit on chip
+static ResGeom resident_geom(int L, size_t smem_limit) {
+  ResGeom rg{};
+  const int cs = (L >= 2 * RES_CS_MAX) ? RES_CS_MAX : 1;
+  rg.rows_max = (L + cs - 1) / cs;
+  rg.prow = rg.rows_max + 4;
+  rg.QR = (L + 3) / 4;
+  rg.pitch = (RG + rg.QR * 4 + RG + 15) / 16 * 16;
+  const int quads = rg.rows_max * rg.QR;
+  rg.threads = std::max(64, std::min(RES_THREADS, (quads + 31) / 32 * 32));
+  rg.CS = (ResSmem(rg).total <= smem_limit) ? cs : 0;
+  return rg;
+}
+
 static int make_map(CUtensorMap *map, void *base, uint64_t row_bytes, uint64_t n_rows, uint64_t n_rep,
                     uint64_t rep_stride_bytes, uint32_t box_bytes, uint32_t box_rows) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -344,6 +370,22 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     (void)r0;
     h->fast = ok;
   }
+  // resident path (spgg_resident.cuh): whole lattice, int8 throughput mode, Q-learning, on-chip fit
+  {
+    cudaDeviceProp prop0;
+    CUDA_TRY(cudaGetDeviceProperties(&prop0, device));
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pick_res(h->M, h->action)));
+    const ResGeom rg = resident_geom(g.L, prop0.sharedMemPerBlockOptin - fa.sharedSizeBytes - 1024);
+    h->resident = (h->mode == MODE_F32_I8) && g.wrap_rows && p0.row0 == 0 && rg.CS > 0 &&
+                  p0.algorithm == SPGG_ALGO_QLEARNING && getenv("SPGG_NO_RESIDENT") == nullptr;
+    if (h->resident) {
+      h->rgeo = rg;
+      h->smem_res = ResSmem(rg).total;
+      CUDA_TRY(cudaFuncSetAttribute(pick_res(h->M, h->action), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)h->smem_res));
+    }
+  }
   g.TR = h->fast ? FTR : (g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4));
   h->threads = h->fast ? FTHREADS : 32 * std::min(8, g.TR);
   g.n_tx = (g.L + TC - 1) / TC;
@@ -452,7 +494,11 @@ static int finish_pending(spgg_handle *h) {
       e = std::max(e * h->params[r].epsilon_decay, h->params[r].epsilon_min);  // algorithms.py:42
     h->eps_cur[r] = e;
   }
-  if (h->n_rep == 1 && stop[0] >= 0 && stop[0] < t_end) {
+  if (h->pend_resident) {
+    // the resident kernel wrote every replica's final state into plane set `cur`
+    h->iter = (h->n_rep == 1 && stop[0] >= 0 && stop[0] < t_end) ? (long long)stop[0] : t_end;
+    h->pend_resident = false;
+  } else if (h->n_rep == 1 && stop[0] >= 0 && stop[0] < t_end) {
     h->cur = h->pend_cur0 ^ (int)((stop[0] - h->pend_t0) & 1);
     h->iter = stop[0];
   } else {
@@ -758,9 +804,48 @@ extern "C" int spgg_end_steps(spgg_t *h, void *stream_) {
   return SPGG_OK;  // bookkeeping is finished lazily by the next synchronising call
 }
 
+// the whole chunk in one launch: one cluster per replica keeps its lattice in shared memory
+static int resident_chunk(spgg_handle *h, int n_steps, cudaStream_t st) {
+  RArgs a;
+  a.g = h->g;
+  a.rg = h->rgeo;
+  a.rc = h->d_rc;
+  a.Q = h->d_Q;
+  a.R = h->d_R[h->cur];
+  a.S = h->d_S[h->cur];
+  a.stats = h->d_stats;
+  a.stop_at = h->d_stop;
+  a.thr_tab = h->d_thr;
+  a.t0 = (int)h->pend_t0;
+  a.n_steps = n_steps;
+  a.cap = h->cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(h->rgeo.CS * h->n_rep));
+  cfg.blockDim = dim3((unsigned)h->rgeo.threads);
+  cfg.dynamicSmemBytes = h->smem_res;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)h->rgeo.CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res(h->M, h->action), a));
+  h->launches += 1;
+  h->pend_rel = n_steps;
+  h->pend_resident = true;
+  return SPGG_OK;
+}
+
 extern "C" int spgg_step(spgg_t *h, int n_steps, void *stream_) {
   int rcode = spgg_begin_steps(h, n_steps, stream_);
   if (rcode) return rcode;
+  if (h->resident && !h->d_u) {  // replayed draws go through the general kernel
+    rcode = resident_chunk(h, n_steps, (cudaStream_t)stream_);
+    if (rcode) return rcode;
+    return spgg_end_steps(h, stream_);
+  }
   rcode = spgg_phase_kernel(h, 0, 1, stream_);  // choose the action of iteration iter+1
   for (int s = 1; s <= n_steps && !rcode; ++s) {
     rcode = spgg_phase_gmax(h, stream_);

@@ -1,0 +1,496 @@
+// SPGG lattice step for sm_100a - lattice-resident cluster kernel (small lattices).
+//
+// The reference's own workloads are small lattices run for very many iterations
+// (default_config.yaml: L=100, 100001 iterations; figure sweeps: L=100/200).
+// At that size the two-kernels-per-iteration scheme of spgg_kernels.cuh / spgg_fast.cuh is
+// bound by launch latency, not by memory.  Here ONE thread-block cluster owns one replica
+// for a whole chunk of iterations:
+//
+//   * the lattice state - Q (16 B/site, four float4 planes), reputation, reward codes and
+//     strategies (byte planes, ping-pong) - lives in the shared memory of the cluster's CTAs
+//     (row blocks), loaded from HBM once per chunk and written back once;
+//   * the two ghost rows a CTA needs from each neighbour are PUSHED into the neighbour's
+//     shared memory through DSMEM by the thread that produces them;
+//   * the lattice-global max |reward difference| (spgg.py:488) is an all-to-all of one float
+//     per CTA through DSMEM; the early-exit test (spgg.py:405) the same with one counter;
+//   * two cluster barriers per iteration replace two kernel launches.
+//
+// Arithmetic, Philox counters and statistics are those of k_step<ModeF32I8> / k_gmax
+// (Q-learning, algorithms.py:96-133), so S, R and Q are bit-identical to the other two paths.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "spgg_kernels.cuh"
+
+namespace spgg {
+namespace cg = cooperative_groups;
+
+constexpr int RES_THREADS = 512;  // upper bound; small lattices launch fewer
+constexpr int RES_CS_MAX = 8;     // portable cluster size
+constexpr int RG = 4;             // ghost columns (bytes) on each side of a shared-memory plane row
+constexpr int RES_NI = 18;        // integer statistics per thread
+constexpr int RES_NF = 10;        // fp32 statistics per thread
+constexpr int RES_NRED = RES_NI + RES_NF;
+
+struct ResGeom {
+  int CS;        // CTAs per cluster = row blocks per replica
+  int rows_max;  // rows of the largest block: ceil(L / CS)
+  int prow;      // plane rows: rows_max + 4 (two ghost rows each side)
+  int pitch;     // bytes per plane row: RG + roundup(L,4) + RG, rounded up to 16
+  int QR;        // quads (4 consecutive sites) per row: ceil(L / 4)
+  int threads;
+};
+
+// byte offsets of the per-CTA shared-memory planes (identical in every CTA of a cluster, so a
+// local offset is valid in a neighbour's window)
+struct ResSmem {
+  size_t q, val, code[2], R[2], C[2], N, tab, redf, redi, gmx, nsel, part, total;
+  __host__ __device__ explicit ResSmem(const ResGeom &rg) {
+    const size_t nq = (size_t)rg.rows_max * rg.QR * 16;  // one float4 plane (one Q entry, 4 sites per element)
+    const size_t nb = (size_t)rg.prow * rg.pitch;
+    size_t o = 0;
+    q = o; o += 4 * nq;
+    val = o; o += 4 * nb;
+    for (int i = 0; i < 2; ++i) { code[i] = o; o += nb; }
+    for (int i = 0; i < 2; ++i) { R[i] = o; o += nb; }
+    for (int i = 0; i < 2; ++i) { C[i] = o; o += nb; }
+    N = o; o += nb;
+    tab = o; o += 256 * sizeof(float);
+    redf = o; o += sizeof(float) * (RES_THREADS / 32) * RES_NF;
+    redi = o; o += sizeof(unsigned) * (RES_NI + 2);
+    gmx = o; o += sizeof(float) * RES_CS_MAX;
+    nsel = o; o += sizeof(unsigned) * RES_CS_MAX;
+    o = (o + 15) / 16 * 16;
+    part = o; o += sizeof(double) * RES_CS_MAX * RES_NRED;
+    total = (o + 15) / 16 * 16;
+  }
+};
+
+struct RArgs {
+  Geom g;
+  ResGeom rg;
+  const RepConst *rc;
+  void *Q;            // float4[n_rep][L*L]
+  void *R;            // int8 planes holding the current state (read at start, written at end)
+  uint32_t *S;        // strategy bit planes, same
+  double *stats;      // [n_rep][cap][NSTAT]
+  int *stop_at;       // [n_rep]
+  const uint32_t *thr_tab;  // [cap+1][n_rep]: ceil(eps*2^24) used at iteration t0 + idx
+  int t0;             // iterations completed before this launch
+  int n_steps;
+  int cap;
+};
+
+template <int M, bool ACTION>
+__global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
+  constexpr int NK = (M == 2) ? 12 : 4;
+  cg::cluster_group cluster = cg::this_cluster();
+  const Geom &g = a.g;
+  const ResGeom &rg = a.rg;
+  const int CS = rg.CS;
+  const int rep = blockIdx.x / CS;
+  const int rank = (int)cluster.block_rank();
+  const int L = g.L, pitch = rg.pitch, QR = rg.QR;
+  const int W = pitch >> 2;  // 32-bit words per plane row
+  const int base_rows = L / CS, rem = L % CS;
+  const int nrow = base_rows + (rank < rem ? 1 : 0);
+  const int row_start = rank * base_rows + min(rank, rem);
+  const int up = (rank + CS - 1) % CS, down = (rank + 1) % CS;
+  const int nrow_up = base_rows + (up < rem ? 1 : 0);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ResSmem lay(rg);
+  float4 *sQ = reinterpret_cast<float4 *>(smem + lay.q);
+  const int q_plane = rg.rows_max * QR;  // float4 elements per Q plane
+  float *s_val = reinterpret_cast<float *>(smem + lay.val);
+  uint8_t *s_N = smem + lay.N;
+  float *s_tab = reinterpret_cast<float *>(smem + lay.tab);
+  float *s_ratio = s_tab + 128;
+  float *s_redf = reinterpret_cast<float *>(smem + lay.redf);
+  unsigned *s_redi = reinterpret_cast<unsigned *>(smem + lay.redi);  // [RES_NI] sums, [RES_NI] = block max
+  float *s_gmx = reinterpret_cast<float *>(smem + lay.gmx);
+  unsigned *s_nsel = reinterpret_cast<unsigned *>(smem + lay.nsel);
+  double *s_part = reinterpret_cast<double *>(smem + lay.part);
+  const int o_code0 = (int)lay.code[0], o_R0 = (int)lay.R[0], o_C0 = (int)lay.C[0];
+  const int nb = rg.prow * pitch;  // bytes per byte plane; set 1 follows set 0
+  __shared__ RepConst s_rc;
+  __shared__ double s_fold[RES_NRED];
+
+  // ---- zero every plane (cells that are neither sites nor ghosts stay zero for good: the
+  // byte-parallel group count below must not see junk), constants, accumulators
+  for (size_t i = (size_t)tid * 16; i < lay.total; i += (size_t)nthr * 16)
+    *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (int)(sizeof(RepConst) / 4); i += nthr)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  __syncthreads();
+  for (int i = tid; i < 128; i += nthr) {
+    s_tab[i] = s_rc.rewtab[i];
+    s_ratio[i] = s_rc.ratiotab[i];
+  }
+  const RepConst &rc = s_rc;
+
+  // ---- load the state of this row block (+ two ghost rows each side, two ghost columns)
+  float4 *Qg = reinterpret_cast<float4 *>(a.Q) + (long long)rep * g.site_stride;
+  int8_t *Rg = reinterpret_cast<int8_t *>(a.R) + (long long)rep * g.plane_stride;
+  uint32_t *Sg = a.S + (long long)rep * g.bits_stride;
+  {
+    uint8_t *R0 = smem + o_R0, *C0 = smem + o_C0;
+    const int wc = L + 4, ncell = (nrow + 4) * wc;
+    for (int e = tid; e < ncell; e += nthr) {
+      const int rr = e / wc - 2, cc = e % wc - 2;
+      int grow = row_start + rr, gcol = cc;
+      grow += (grow < 0) ? L : 0; grow -= (grow >= L) ? L : 0;
+      gcol += (gcol < 0) ? L : 0; gcol -= (gcol >= L) ? L : 0;
+      const int idx = (rr + 2) * pitch + RG + cc;
+      R0[idx] = (uint8_t)Rg[(long long)(grow + GH) * g.pitchB + CPAD + gcol];
+      const uint32_t w = Sg[(long long)(grow + GH) * g.pitchW + WPAD + (gcol >> 5)];
+      C0[idx] = (uint8_t)(((w >> (gcol & 31)) & 1u) ^ 1u);
+    }
+    float *sQf = reinterpret_cast<float *>(sQ);
+    for (int e = tid; e < nrow * L; e += nthr) {
+      const int rr = e / L, cc = e % L;
+      const float4 v = Qg[(long long)(row_start + rr) * L + cc];
+      const int o = (rr * QR + (cc >> 2)) * 4 + (cc & 3);
+      sQf[o] = v.x;
+      sQf[(q_plane * 4) + o] = v.y;
+      sQf[(q_plane * 8) + o] = v.z;
+      sQf[(q_plane * 12) + o] = v.w;
+    }
+  }
+  unsigned char *smem_up = cluster.map_shared_rank(smem, up);
+  unsigned char *smem_dn = cluster.map_shared_rank(smem, down);
+  __syncthreads();
+  cluster.sync();  // every CTA of the cluster runs and has zeroed its planes before anyone pushes ghosts
+
+  // ---- loop-invariant iteration patterns: plane words (row, word) and quads (row, quad)
+  const int w_r0 = tid / W, w_c0 = tid % W, w_dr = nthr / W, w_dc = nthr % W;
+  const int q_r0 = tid / QR, q_c0 = tid % QR, q_dr = nthr / QR, q_dc = nthr % QR;
+  const long long n_sites = (long long)L * L;
+
+  int stop = a.stop_at[rep];
+  int cur = 0;
+  for (int s = 0; s <= a.n_steps; ++s) {
+    const int j = a.t0 + s;
+    if (stop >= 0 && j > stop) break;
+    const bool upd = s > 0;
+    const bool sel = (s < a.n_steps) && !(stop >= 0 && j == stop);
+    const uint32_t thr = sel ? __ldg(a.thr_tab + (long long)(s + 1) * g.n_rep + rep) : 0u;
+    const uint8_t *codeC = smem + o_code0 + cur * nb;
+    const uint8_t *Rc = smem + o_R0 + cur * nb;
+    const uint8_t *Cc = smem + o_C0 + cur * nb;
+    const int o_code_n = o_code0 + (cur ^ 1) * nb, o_R_n = o_R0 + (cur ^ 1) * nb, o_C_n = o_C0 + (cur ^ 1) * nb;
+
+    // ---- phase 1: cooperators per group (spgg.py:23-36) for the block and a one-site ring,
+    // four sites per word; reward of every site the block can see (own rows + M ghost rows)
+    {
+      const uint32_t *Cw = reinterpret_cast<const uint32_t *>(Cc);
+      uint32_t *Nw = reinterpret_cast<uint32_t *>(s_N);
+      int rr = w_r0, wq = w_c0;
+      while (rr < nrow + 2) {  // plane rows 1 .. nrow+2  (local rows -1 .. nrow)
+        const int i4 = (rr + 1) * W + wq;
+        const uint32_t c = Cw[i4];
+        const uint32_t lw = __funnelshift_l(Cw[i4 - 1], c, 8), rw = __funnelshift_r(c, Cw[i4 + 1], 8);
+        Nw[i4] = c + Cw[i4 - W] + Cw[i4 + W] + lw + rw;
+        rr += w_dr; wq += w_dc;
+        if (wq >= W) { wq -= W; rr += 1; }
+      }
+      if (upd) {
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(codeC);
+        float4 *vw = reinterpret_cast<float4 *>(s_val);
+        rr = w_r0; wq = w_c0;
+        while (rr < nrow + 2 * M) {  // plane rows 2-M .. nrow+1+M
+          const int i4 = (rr + 2 - M) * W + wq;
+          const uint32_t c = cw[i4];
+          vw[i4] = make_float4(s_tab[(c >> 1) & 127u], s_tab[(c >> 9) & 127u], s_tab[(c >> 17) & 127u],
+                               s_tab[c >> 25]);
+          rr += w_dr; wq += w_dc;
+          if (wq >= W) { wq -= W; rr += 1; }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: lattice-global max |reward difference| (spgg.py:486-488): each unordered
+    // neighbour pair once, block max, all-to-all through DSMEM
+    float inv_den = 0.0f, gm = 0.0f;
+    if (upd) {
+      float lmax = 0.0f;
+      int rr = q_r0, qc = q_c0;
+      while (rr < nrow) {
+        const int base = (rr + 2) * pitch + RG + 4 * qc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (4 * qc + k < L) {
+            const int idx = base + k;
+            const float vx = s_val[idx];
+#pragma unroll
+            for (int z = 0; z < NK; ++z) {
+              if (z == 1 || z == 3 || z == 5 || z == 7 || z == 10 || z == 11) continue;  // mirror images
+              const float d = fabsf(__fsub_rn(s_val[idx - c_off[z][0] * pitch - c_off[z][1]], vx));
+              lmax = d > lmax ? d : lmax;
+            }
+          }
+        }
+        rr += q_dr; qc += q_dc;
+        if (qc >= QR) { qc -= QR; rr += 1; }
+      }
+      const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
+      if (lane == 0) atomicMax(&s_redi[RES_NI], wm);
+      __syncthreads();
+      if (tid < CS) {
+        float *dst = reinterpret_cast<float *>(cluster.map_shared_rank(smem, tid) + lay.gmx);
+        dst[rank] = __uint_as_float(s_redi[RES_NI]);
+      }
+      cluster.sync();
+      for (int k = 0; k < CS; ++k) gm = fmaxf(gm, s_gmx[k]);
+      inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));  // spgg.py:489 denominator
+    }
+
+    // ---- phase 3: finish iteration j (TD + neighbour-aware update, statistics), choose the
+    // action of iteration j+1, update the reputation, emit the reward code of j+1
+    // packed per-thread counters (a thread visits at most 128 sites per iteration): 8-bit class
+    // counts (class = C_old*2 + coop), 16-bit SigmaN sums per class, 10-bit group histogram
+    unsigned pk_n = 0;
+    unsigned long long pk_sn = 0, pk_grp = 0;
+    unsigned n_best = 0, n_best2 = 0, n_sel_coop = 0;
+    int tri = 0;
+    float tq[4] = {0.f, 0.f, 0.f, 0.f}, tqc[4] = {0.f, 0.f, 0.f, 0.f};
+    float tni = 0.f, tratio = 0.f;
+    {
+      int rr = q_r0, qc = q_c0;
+      while (rr < nrow) {
+        const int base = (rr + 2) * pitch + RG + 4 * qc;
+        const int qi = rr * QR + qc;
+        float qv[4][4];  // [entry 2s+a][site of the quad]
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          const float4 v = sQ[z * q_plane + qi];
+          qv[z][0] = v.x; qv[z][1] = v.y; qv[z][2] = v.z; qv[z][3] = v.w;
+        }
+        uint32_t w4[4] = {0, 0, 0, 0};
+        if (sel)  // counter = (column / 4, global row, iteration, 0): one call per quad
+          philox4x32_10((uint32_t)qc, (uint32_t)(row_start + rr), (uint32_t)(j + 1), 0u, rc.seed_lo,
+                        rc.seed_hi, w4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = 4 * qc + k;
+          if (col >= L) continue;
+          const int idx = base + k;
+          float q0_ = qv[0][k], q1_ = qv[1][k], q2_ = qv[2][k], q3_ = qv[3][k];
+          const int r_old = (int)(int8_t)Rc[idx];
+          const int Ccur = Cc[idx];
+          int s_new;  // post-action state of iteration j == pre-action state of j+1 (spgg.py:423 vs 409)
+          if constexpr (ACTION) {
+            s_new = Ccur;
+          } else {
+            int acc = r_old;
+#pragma unroll
+            for (int z = 0; z < NK; ++z) acc += (int)(int8_t)Rc[idx - c_off[z][0] * pitch - c_off[z][1]];
+            s_new = acc > 0;
+          }
+          tri += r_old;
+          if (upd) {
+            const unsigned code = codeC[idx];
+            const int sO = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
+            const int act = coop ^ 1;
+            const float vx = s_val[idx];
+            float best = 0.0f;
+            int bidx = idx, kstar = 0;
+#pragma unroll
+            for (int z = 0; z < NK; ++z) {  // first arg-max wins, spgg.py:486-494
+              const int nidx = idx - c_off[z][0] * pitch - c_off[z][1];
+              const float d = __fsub_rn(s_val[nidx], vx);
+              if (z == 0 || d > best) { best = d; bidx = nidx; kstar = z; }
+            }
+            const bool same = (((codeC[bidx] >> 1) & 1u) == (unsigned)coop);
+            const int e = 2 * sO + act;
+            const float qe = sel4<float>(e, q0_, q1_, q2_, q3_);
+            const float na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
+            const float td = __fsub_rn(__fmaf_rn(rc.gamma_f, fmaxf(na, nb), vx), qe);   // algorithms.py:125-128
+            const float qtd = __fmaf_rn(rc.alpha_f, td, qe);                             // algorithms.py:131
+            const float lam = __fmul_rn(__fmul_rn(rc.kappa_f, fmaxf(0.0f, best)), inv_den);  // spgg.py:489
+            const float nu = same ? lam : -lam;                                          // spgg.py:494-495
+            const float na2 = (s_new == sO && act == 0) ? qtd : na;
+            const float nb2 = (s_new == sO && act == 1) ? qtd : nb;
+            const float td2 = __fsub_rn(__fmaf_rn(rc.gamma_f, fmaxf(na2, nb2), vx), qtd);
+            const float qfin = __fadd_rn(qtd, nu);                                       // spgg.py:509
+            const float an = fabsf(nu);
+            tni += __fdividef(an, fabsf(rc.alpha_f * td2) + an + 1e-8f) * 100.0f;        // spgg.py:512
+            pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
+            if (rc.has_ratio && coop) tratio += s_ratio[code >> 1];
+            q0_ = (e == 0) ? qfin : q0_;
+            q1_ = (e == 1) ? qfin : q1_;
+            q2_ = (e == 2) ? qfin : q2_;
+            q3_ = (e == 3) ? qfin : q3_;
+            pk_n += 1u << (8 * (wasC * 2 + coop));
+            if (best > 0.0f) { n_best += 1u; n_best2 += (kstar >= 4); }
+            pk_grp += 1ull << (10 * (5 - (int)s_N[idx]));                                              // spgg.py:586-592
+            const float m = wasC ? 1.0f : 0.0f;
+            tq[0] += q0_; tq[1] += q1_; tq[2] += q2_; tq[3] += q3_;
+            tqc[0] = fmaf(m, q0_, tqc[0]); tqc[1] = fmaf(m, q1_, tqc[1]);
+            tqc[2] = fmaf(m, q2_, tqc[2]); tqc[3] = fmaf(m, q3_, tqc[3]);
+            qv[0][k] = q0_; qv[1][k] = q1_; qv[2][k] = q2_; qv[3][k] = q3_;
+          }
+          if (sel) {
+            const int explore = (w4[k] >> 8) < thr;                                      // algorithms.py:105
+            const int rnd = (int)(w4[k] & 1u);                                           // algorithms.py:108
+            const float ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
+            const int greedy = (gb > ga) ? 1 : 0;                                        // argmax, tie -> C
+            const int a_new = explore ? rnd : greedy;
+            n_sel_coop += (a_new == 0);
+            int t = r_old + (a_new == 0 ? rc.gain_i : -rc.loss_i);                       // spgg.py:321-323
+            t = max(t, rc.rmin_i);
+            t = min(t, rc.rmax_i);
+            const int sn = (int)s_N[idx] + (int)s_N[idx - pitch] + (int)s_N[idx + pitch] + (int)s_N[idx - 1] +
+                           (int)s_N[idx + 1];
+            const uint8_t cnew = (uint8_t)((sn << 3) | (Ccur << 2) | ((a_new ^ 1) << 1) | s_new);
+            const uint8_t rnew = (uint8_t)(int8_t)t, Cnew = (uint8_t)(a_new ^ 1);
+            // own cell + periodic column image; rows within two of a block edge also land in the
+            // neighbour block's ghost rows (DSMEM)
+            const int gdx = (col < GC) ? L : ((col >= L - GC) ? -L : 0);
+            auto put = [&](unsigned char *basep, int at) {
+              basep[o_code_n + at] = cnew; basep[o_R_n + at] = rnew; basep[o_C_n + at] = Cnew;
+              if (gdx) {
+                basep[o_code_n + at + gdx] = cnew; basep[o_R_n + at + gdx] = rnew; basep[o_C_n + at + gdx] = Cnew;
+              }
+            };
+            put(smem, idx);
+            if (rr < 2) put(smem_up, (nrow_up + rr + 2) * pitch + RG + col);
+            if (rr >= nrow - 2) put(smem_dn, (rr - nrow + 2) * pitch + RG + col);
+          }
+        }
+        if (upd) {
+#pragma unroll
+          for (int z = 0; z < 4; ++z) sQ[z * q_plane + qi] = make_float4(qv[z][0], qv[z][1], qv[z][2], qv[z][3]);
+        }
+        rr += q_dr; qc += q_dc;
+        if (qc >= QR) { qc -= QR; rr += 1; }
+      }
+    }
+
+    // ---- block statistics: exact integers through redux + shared atomics, fp32 sums per warp
+    {
+      unsigned iv[RES_NI];
+#pragma unroll
+      for (int z = 0; z < 4; ++z) {
+        iv[z] = (pk_n >> (8 * z)) & 0xffu;
+        iv[4 + z] = (unsigned)((pk_sn >> (16 * z)) & 0xffffull);
+      }
+#pragma unroll
+      for (int z = 0; z < 6; ++z) iv[8 + z] = (unsigned)((pk_grp >> (10 * z)) & 0x3ffull);
+      iv[14] = n_best; iv[15] = n_best2; iv[16] = n_sel_coop; iv[17] = (unsigned)tri;
+#pragma unroll
+      for (int z = 0; z < RES_NI; ++z) {
+        const unsigned x = __reduce_add_sync(0xffffffffu, iv[z]);  // two's complement: exact for the signed sum too
+        if (lane == 0 && x) atomicAdd(&s_redi[z], x);
+      }
+      if (upd) {
+        const float fv[RES_NF] = {tq[0], tq[1], tq[2], tq[3], tqc[0], tqc[1], tqc[2], tqc[3], tni, tratio};
+#pragma unroll
+        for (int z = 0; z < RES_NF; ++z) {
+          float x = fv[z];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+          if (lane == 0) s_redf[warp * RES_NF + z] = x;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < RES_NRED) {
+      double x = 0.0;
+      if (tid < RES_NI) {
+        x = (tid == RES_NI - 1) ? (double)(int)s_redi[tid] : (double)s_redi[tid];
+      } else if (upd) {
+        for (int w = 0; w < nwarp; ++w) x += (double)s_redf[w * RES_NF + (tid - RES_NI)];
+      }
+      double *dst = reinterpret_cast<double *>(cluster.map_shared_rank(smem, 0) + lay.part);
+      dst[rank * RES_NRED + tid] = x;
+    } else if (tid >= 32 && tid < 32 + CS) {
+      unsigned *dst = reinterpret_cast<unsigned *>(cluster.map_shared_rank(smem, tid - 32) + lay.nsel);
+      dst[rank] = s_redi[16];
+    }
+    cluster.sync();  // ghost rows, partial rows and counters of every block have landed
+
+    if (sel) {
+      // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405)
+      long long tot = 0;
+      for (int k = 0; k < CS; ++k) tot += s_nsel[k];
+      if (tot == 0 || tot == n_sites) stop = j + 1;
+      cur ^= 1;
+    }
+    if (rank == 0 && warp == 0) {
+      // fold the block rows in a fixed order ...
+      if (lane < RES_NRED) {
+        double x = 0.0;
+        for (int k = 0; k < CS; ++k) x += s_part[k * RES_NRED + lane];
+        s_fold[lane] = x;
+      }
+      __syncwarp();
+    }
+    if (rank == 0 && tid == 0) {
+      // ... and finish the statistics row like k_step does
+      const double *f = s_fold;
+      double *row = a.stats + ((long long)rep * a.cap + s) * NSTAT;
+      row[ST_SUM_R] = f[17] * rc.rq;
+      if (upd) {
+        const double nc[4] = {f[0], f[1], f[2], f[3]};
+        double Pc[4];
+        for (int z = 0; z < 4; ++z) {  // exact-count payoff sums per class
+          const double C = (z >> 1) ? 1.0 : 0.0;
+          Pc[z] = ((rc.rc * f[4 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) / rc.span;
+        }
+        row[ST_NC_OLD] = nc[2] + nc[3];
+        row[ST_N_CD] = nc[2];
+        row[ST_N_DC] = nc[1];
+        row[ST_NC_NEW] = nc[1] + nc[3];
+        const double sumP = Pc[0] + Pc[1] + Pc[2] + Pc[3];
+        row[ST_SUM_P] = sumP;
+        row[ST_SUM_P_C] = Pc[2] + Pc[3];
+        row[ST_SUM_P_D] = Pc[0] + Pc[1];
+        row[ST_SUM_WP_P] = rc.wP * sumP;
+        row[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
+        row[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
+        row[ST_SUM_RATIO] = f[27];
+        for (int z = 0; z < 6; ++z) row[ST_GROUP0 + z] = f[8 + z];
+        for (int z = 0; z < 4; ++z) {
+          row[ST_SUM_Q + z] = f[18 + z];
+          row[ST_SUM_Q_C + z] = f[22 + z];
+          row[ST_SUM_Q_D + z] = f[18 + z] - f[22 + z];
+        }
+        row[ST_SUM_NI] = f[26];
+        row[ST_N_BEST_POS] = f[14];
+        row[ST_N_BEST_2ND] = f[15];
+        row[ST_GMAX] = (double)gm;
+      }
+    }
+    if (tid <= RES_NI) s_redi[tid] = 0u;  // next use is behind the next block barrier
+  }
+
+  // ---- write the state back: Q, reputation, strategy bits (ghost cells included, so the
+  // per-iteration kernels can continue from these planes)
+  if (rank == 0 && tid == 0) a.stop_at[rep] = stop;
+  {
+    const uint8_t *Rc = smem + o_R0 + cur * nb;
+    const uint8_t *Cc = smem + o_C0 + cur * nb;
+    const float *sQf = reinterpret_cast<const float *>(sQ);
+    for (int e = tid; e < nrow * L; e += nthr) {
+      const int rr = e / L, cc = e % L;
+      const int o = (rr * QR + (cc >> 2)) * 4 + (cc & 3);
+      Qg[(long long)(row_start + rr) * L + cc] =
+          make_float4(sQf[o], sQf[(q_plane * 4) + o], sQf[(q_plane * 8) + o], sQf[(q_plane * 12) + o]);
+      store_cell<int8_t>(Rg, g, row_start + rr, cc, (int8_t)Rc[(rr + 2) * pitch + RG + cc]);
+    }
+    const int nW = (L + 31) >> 5;
+    for (int e = tid; e < nrow * nW; e += nthr) {
+      const int rr = e / nW, wi = e % nW;
+      uint32_t word = 0;
+      const int c0 = wi * 32, n = min(32, L - c0);
+      for (int b = 0; b < n; ++b) word |= (uint32_t)(Cc[(rr + 2) * pitch + RG + c0 + b] ^ 1u) << b;
+      store_bits_word(Sg, g, row_start + rr, wi, word);
+    }
+  }
+}
+
+}  // namespace spgg
