@@ -225,9 +225,13 @@ static size_t gfast_smem(int M) { return M == 2 ? GmaxSmem<2>::kTotal : GmaxSmem
 
 // ---------------------------------------------------------------- resident path plumbing
 typedef void (*res_fn_t)(RArgs);
-static res_fn_t pick_res(int M, int action) {
-  if (M == 2) return action ? k_resident<2, true> : k_resident<2, false>;
-  return action ? k_resident<1, true> : k_resident<1, false>;
+template <bool FULL>
+static res_fn_t pick_res2(int M, int action) {
+  if (M == 2) return action ? k_resident<2, true, FULL> : k_resident<2, false, FULL>;
+  return action ? k_resident<1, true, FULL> : k_resident<1, false, FULL>;
+}
+static res_fn_t pick_res(int M, int action, int L) {
+  return (L % 4 == 0) ? pick_res2<true>(M, action) : pick_res2<false>(M, action);
 }
 // geometry of the cluster decomposition, or CS = 0 when the lattice does not fit on chip
 static ResGeom resident_geom(int L, size_t smem_limit) {
@@ -375,14 +379,14 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     cudaDeviceProp prop0;
     CUDA_TRY(cudaGetDeviceProperties(&prop0, device));
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, pick_res(h->M, h->action)));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pick_res(h->M, h->action, h->g.L)));
     const ResGeom rg = resident_geom(g.L, prop0.sharedMemPerBlockOptin - fa.sharedSizeBytes - 1024);
     h->resident = (h->mode == MODE_F32_I8) && g.wrap_rows && p0.row0 == 0 && rg.CS > 0 &&
                   p0.algorithm == SPGG_ALGO_QLEARNING && getenv("SPGG_NO_RESIDENT") == nullptr;
     if (h->resident) {
       h->rgeo = rg;
       h->smem_res = ResSmem(rg).total;
-      CUDA_TRY(cudaFuncSetAttribute(pick_res(h->M, h->action), cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_TRY(cudaFuncSetAttribute(pick_res(h->M, h->action, h->g.L), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)h->smem_res));
     }
   }
@@ -831,7 +835,7 @@ static int resident_chunk(spgg_handle *h, int n_steps, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res(h->M, h->action), a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res(h->M, h->action, h->g.L), a));
   h->launches += 1;
   h->pend_rel = n_steps;
   h->pend_resident = true;

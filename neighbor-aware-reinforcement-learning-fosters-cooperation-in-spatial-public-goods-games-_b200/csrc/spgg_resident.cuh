@@ -20,6 +20,8 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "spgg_kernels.cuh"
 
 namespace spgg {
@@ -81,7 +83,63 @@ struct RArgs {
   int cap;
 };
 
-template <int M, bool ACTION>
+// Rewards around a quad (4 consecutive sites of a row, first plane index `base`) held in
+// registers: c[i] = own row, column base-2+i; u[i] / d[i] = row above / below, column base-1+i;
+// u2[i] / d2[i] = two rows above / below, column base+i.  M=1 touches c[1..6], u[1..4], d[1..4].
+template <int M>
+struct ValWin {
+  float c[8], u[6], d[6], u2[4], d2[4];
+};
+template <int M, bool BELOW>
+__device__ __forceinline__ void load_win(ValWin<M> &w, const float *V, int base, int pitch) {
+  const float4 c4 = *reinterpret_cast<const float4 *>(V + base);
+  w.c[2] = c4.x; w.c[3] = c4.y; w.c[4] = c4.z; w.c[5] = c4.w;
+  w.c[1] = V[base - 1];
+  const float4 u4 = *reinterpret_cast<const float4 *>(V + base - pitch);
+  w.u[1] = u4.x; w.u[2] = u4.y; w.u[3] = u4.z; w.u[4] = u4.w;
+  if constexpr (M == 2) {
+    w.c[0] = V[base - 2];
+    w.u[0] = V[base - pitch - 1];
+    w.u[5] = V[base - pitch + 4];
+    const float4 t4 = *reinterpret_cast<const float4 *>(V + base - 2 * pitch);
+    w.u2[0] = t4.x; w.u2[1] = t4.y; w.u2[2] = t4.z; w.u2[3] = t4.w;
+  }
+  if constexpr (BELOW) {
+    w.c[6] = V[base + 4];
+    const float4 d4 = *reinterpret_cast<const float4 *>(V + base + pitch);
+    w.d[1] = d4.x; w.d[2] = d4.y; w.d[3] = d4.z; w.d[4] = d4.w;
+    if constexpr (M == 2) {
+      w.c[7] = V[base + 5];
+      w.d[0] = V[base + pitch - 1];
+      w.d[5] = V[base + pitch + 4];
+      const float4 t4 = *reinterpret_cast<const float4 *>(V + base + 2 * pitch);
+      w.d2[0] = t4.x; w.d2[1] = t4.y; w.d2[2] = t4.z; w.d2[3] = t4.w;
+    }
+  }
+}
+// reward of neighbour z (order of c_off: the value at (row - dx, col - dy)) of site k of the quad
+template <int M>
+__device__ __forceinline__ float win_nbr(const ValWin<M> &w, int k, int z) {
+  switch (z) {
+    case 0: return w.u[1 + k];
+    case 1: return w.d[1 + k];
+    case 2: return w.c[1 + k];
+    case 3: return w.c[3 + k];
+    case 4: return w.u2[k];
+    case 5: return w.d2[k];
+    case 6: return w.c[k];
+    case 7: return w.c[4 + k];
+    case 8: return w.u[k];
+    case 9: return w.u[2 + k];
+    case 10: return w.d[k];
+    default: return w.d[2 + k];
+  }
+}
+
+// FULL: L is a multiple of 4, so every quad is complete (no per-site validity branches: the four
+// sites of a quad are independent instruction streams the scheduler can interleave) and the
+// periodic column images are whole words.
+template <int M, bool ACTION, bool FULL>
 __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   constexpr int NK = (M == 2) ? 12 : 4;
   cg::cluster_group cluster = cg::this_cluster();
@@ -117,6 +175,8 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   const int nb = rg.prow * pitch;  // bytes per byte plane; set 1 follows set 0
   __shared__ RepConst s_rc;
   __shared__ double s_fold[RES_NRED];
+  __shared__ int s_noff[12];  // plane-index offset of neighbour z: dx*pitch + dy
+  if (threadIdx.x < 12) s_noff[threadIdx.x] = c_off[threadIdx.x][0] * pitch + c_off[threadIdx.x][1];
 
   // ---- zero every plane (cells that are neither sites nor ghosts stay zero for good: the
   // byte-parallel group count below must not see junk), constants, accumulators
@@ -220,15 +280,16 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       int rr = q_r0, qc = q_c0;
       while (rr < nrow) {
         const int base = (rr + 2) * pitch + RG + 4 * qc;
+        ValWin<M> w;
+        load_win<M, false>(w, s_val, base, pitch);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (4 * qc + k < L) {
-            const int idx = base + k;
-            const float vx = s_val[idx];
+          if (FULL || 4 * qc + k < L) {
+            const float vx = w.c[2 + k];
 #pragma unroll
             for (int z = 0; z < NK; ++z) {
               if (z == 1 || z == 3 || z == 5 || z == 7 || z == 10 || z == 11) continue;  // mirror images
-              const float d = fabsf(__fsub_rn(s_val[idx - c_off[z][0] * pitch - c_off[z][1]], vx));
+              const float d = fabsf(__fsub_rn(win_nbr<M>(w, k, z), vx));
               lmax = d > lmax ? d : lmax;
             }
           }
@@ -258,7 +319,10 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
     int tri = 0;
     float tq[4] = {0.f, 0.f, 0.f, 0.f}, tqc[4] = {0.f, 0.f, 0.f, 0.f};
     float tni = 0.f, tratio = 0.f;
-    {
+    auto phase3 = [&](auto upd_tag, auto sel_tag) {
+      // compile-time copies of the two warp-uniform flags: the steady state (both set) has a
+      // branch-free site body
+      constexpr bool upd = decltype(upd_tag)::value, sel = decltype(sel_tag)::value;
       int rr = q_r0, qc = q_c0;
       while (rr < nrow) {
         const int base = (rr + 2) * pitch + RG + 4 * qc;
@@ -270,41 +334,77 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
           qv[z][0] = v.x; qv[z][1] = v.y; qv[z][2] = v.z; qv[z][3] = v.w;
         }
         uint32_t w4[4] = {0, 0, 0, 0};
-        if (sel)  // counter = (column / 4, global row, iteration, 0): one call per quad
+        if constexpr (sel)  // counter = (column / 4, global row, iteration, 0): one call per quad
           philox4x32_10((uint32_t)qc, (uint32_t)(row_start + rr), (uint32_t)(j + 1), 0u, rc.seed_lo,
                         rc.seed_hi, w4);
+        // the quad's bytes of every plane as one word each
+        const uint32_t Rw = *reinterpret_cast<const uint32_t *>(Rc + base);
+        const uint32_t Cq = *reinterpret_cast<const uint32_t *>(Cc + base);
+        const uint32_t Nq = *reinterpret_cast<const uint32_t *>(s_N + base);
+        uint32_t codeq = 0u;
+        if constexpr (upd) codeq = *reinterpret_cast<const uint32_t *>(codeC + base);
+        const int nvalid = FULL ? 4 : min(4, L - 4 * qc);
+        tri += __dp4a((int)Rw, (int)(0x01010101u >> (8 * (4 - nvalid))), 0);
+        // post-action state of iteration j == pre-action state of j+1 (spgg.py:423 vs 409):
+        // sign of the reputation summed over the site and its neighbours (spgg.py:292-307),
+        // byte-parallel dot products pick the columns each site needs
+        int racc[4] = {0, 0, 0, 0};
+        if constexpr (!ACTION) {
+          constexpr int m1[4] = {0x00000001, 0x00000100, 0x00010000, 0x01000000};
+          constexpr int m3[4] = {0x00000101, 0x00010101, 0x01010100, 0x01010000};
+          const int Ru = *reinterpret_cast<const int *>(Rc + base - pitch);
+          const int Rd = *reinterpret_cast<const int *>(Rc + base + pitch);
+          if constexpr (M == 1) {
+            racc[0] = (int)(int8_t)Rc[base - 1];
+            racc[3] = (int)(int8_t)Rc[base + 4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              racc[k] = __dp4a((int)Rw, m3[k], __dp4a(Ru, m1[k], __dp4a(Rd, m1[k], racc[k])));
+          } else {
+            constexpr int m5[4] = {0x00010101, 0x01010101, 0x01010101, 0x01010100};
+            const int Rl = *reinterpret_cast<const int *>(Rc + base - 4);
+            const int Rr = *reinterpret_cast<const int *>(Rc + base + 4);
+            const int Rul = *reinterpret_cast<const int *>(Rc + base - pitch - 4);
+            const int Rur = *reinterpret_cast<const int *>(Rc + base - pitch + 4);
+            const int Rdl = *reinterpret_cast<const int *>(Rc + base + pitch - 4);
+            const int Rdr = *reinterpret_cast<const int *>(Rc + base + pitch + 4);
+            const int Ru2 = *reinterpret_cast<const int *>(Rc + base - 2 * pitch);
+            const int Rd2 = *reinterpret_cast<const int *>(Rc + base + 2 * pitch);
+            racc[0] = __dp4a(Rl, 0x01010000, __dp4a(Rul, 0x01000000, __dp4a(Rdl, 0x01000000, 0)));
+            racc[1] = __dp4a(Rl, 0x01000000, 0);
+            racc[2] = __dp4a(Rr, 0x00000001, 0);
+            racc[3] = __dp4a(Rr, 0x00000101, __dp4a(Rur, 0x00000001, __dp4a(Rdr, 0x00000001, 0)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              racc[k] = __dp4a((int)Rw, m5[k], __dp4a(Ru, m3[k], __dp4a(Rd, m3[k],
+                        __dp4a(Ru2, m1[k], __dp4a(Rd2, m1[k], racc[k])))));
+          }
+        }
+        ValWin<M> vw;
+        if constexpr (upd) load_win<M, true>(vw, s_val, base, pitch);
+        uint32_t sw = 0, coopw = 0, rneww = 0;  // new state / action / reputation bytes of the quad
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int col = 4 * qc + k;
-          if (col >= L) continue;
+          if (!FULL && col >= L) continue;
           const int idx = base + k;
           float q0_ = qv[0][k], q1_ = qv[1][k], q2_ = qv[2][k], q3_ = qv[3][k];
-          const int r_old = (int)(int8_t)Rc[idx];
-          const int Ccur = Cc[idx];
-          int s_new;  // post-action state of iteration j == pre-action state of j+1 (spgg.py:423 vs 409)
-          if constexpr (ACTION) {
-            s_new = Ccur;
-          } else {
-            int acc = r_old;
-#pragma unroll
-            for (int z = 0; z < NK; ++z) acc += (int)(int8_t)Rc[idx - c_off[z][0] * pitch - c_off[z][1]];
-            s_new = acc > 0;
-          }
-          tri += r_old;
-          if (upd) {
-            const unsigned code = codeC[idx];
+          const int r_old = (int)(int8_t)((Rw >> (8 * k)) & 0xffu);
+          const int Ccur = (int)((Cq >> (8 * k)) & 0xffu);
+          const int s_new = ACTION ? Ccur : (racc[k] > 0);
+          if constexpr (upd) {
+            const unsigned code = (codeq >> (8 * k)) & 0xffu;
             const int sO = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
             const int act = coop ^ 1;
-            const float vx = s_val[idx];
+            const float vx = vw.c[2 + k];
             float best = 0.0f;
-            int bidx = idx, kstar = 0;
+            int kstar = 0;
 #pragma unroll
             for (int z = 0; z < NK; ++z) {  // first arg-max wins, spgg.py:486-494
-              const int nidx = idx - c_off[z][0] * pitch - c_off[z][1];
-              const float d = __fsub_rn(s_val[nidx], vx);
-              if (z == 0 || d > best) { best = d; bidx = nidx; kstar = z; }
+              const float d = __fsub_rn(win_nbr<M>(vw, k, z), vx);
+              if (z == 0 || d > best) { best = d; kstar = z; }
             }
-            const bool same = (((codeC[bidx] >> 1) & 1u) == (unsigned)coop);
+            const bool same = (((codeC[idx - s_noff[kstar]] >> 1) & 1u) == (unsigned)coop);
             const int e = 2 * sO + act;
             const float qe = sel4<float>(e, q0_, q1_, q2_, q3_);
             const float na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
@@ -319,21 +419,21 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
             const float an = fabsf(nu);
             tni += __fdividef(an, fabsf(rc.alpha_f * td2) + an + 1e-8f) * 100.0f;        // spgg.py:512
             pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
-            if (rc.has_ratio && coop) tratio += s_ratio[code >> 1];
+            tratio += s_ratio[code >> 1];  // the table is zero for defecting codes and when w_R = 0
             q0_ = (e == 0) ? qfin : q0_;
             q1_ = (e == 1) ? qfin : q1_;
             q2_ = (e == 2) ? qfin : q2_;
             q3_ = (e == 3) ? qfin : q3_;
             pk_n += 1u << (8 * (wasC * 2 + coop));
             if (best > 0.0f) { n_best += 1u; n_best2 += (kstar >= 4); }
-            pk_grp += 1ull << (10 * (5 - (int)s_N[idx]));                                              // spgg.py:586-592
+            pk_grp += 1ull << (10 * (5 - (int)((Nq >> (8 * k)) & 0xffu)));               // spgg.py:586-592
             const float m = wasC ? 1.0f : 0.0f;
             tq[0] += q0_; tq[1] += q1_; tq[2] += q2_; tq[3] += q3_;
             tqc[0] = fmaf(m, q0_, tqc[0]); tqc[1] = fmaf(m, q1_, tqc[1]);
             tqc[2] = fmaf(m, q2_, tqc[2]); tqc[3] = fmaf(m, q3_, tqc[3]);
             qv[0][k] = q0_; qv[1][k] = q1_; qv[2][k] = q2_; qv[3][k] = q3_;
           }
-          if (sel) {
+          if constexpr (sel) {
             const int explore = (w4[k] >> 8) < thr;                                      // algorithms.py:105
             const int rnd = (int)(w4[k] & 1u);                                           // algorithms.py:108
             const float ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
@@ -343,32 +443,70 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
             int t = r_old + (a_new == 0 ? rc.gain_i : -rc.loss_i);                       // spgg.py:321-323
             t = max(t, rc.rmin_i);
             t = min(t, rc.rmax_i);
-            const int sn = (int)s_N[idx] + (int)s_N[idx - pitch] + (int)s_N[idx + pitch] + (int)s_N[idx - 1] +
-                           (int)s_N[idx + 1];
-            const uint8_t cnew = (uint8_t)((sn << 3) | (Ccur << 2) | ((a_new ^ 1) << 1) | s_new);
-            const uint8_t rnew = (uint8_t)(int8_t)t, Cnew = (uint8_t)(a_new ^ 1);
-            // own cell + periodic column image; rows within two of a block edge also land in the
-            // neighbour block's ghost rows (DSMEM)
-            const int gdx = (col < GC) ? L : ((col >= L - GC) ? -L : 0);
-            auto put = [&](unsigned char *basep, int at) {
-              basep[o_code_n + at] = cnew; basep[o_R_n + at] = rnew; basep[o_C_n + at] = Cnew;
-              if (gdx) {
-                basep[o_code_n + at + gdx] = cnew; basep[o_R_n + at + gdx] = rnew; basep[o_C_n + at + gdx] = Cnew;
-              }
-            };
-            put(smem, idx);
-            if (rr < 2) put(smem_up, (nrow_up + rr + 2) * pitch + RG + col);
-            if (rr >= nrow - 2) put(smem_dn, (rr - nrow + 2) * pitch + RG + col);
+            sw |= (uint32_t)s_new << (8 * k);
+            coopw |= (uint32_t)(a_new ^ 1) << (8 * k);
+            rneww |= ((uint32_t)t & 0xffu) << (8 * k);
           }
         }
-        if (upd) {
+        if constexpr (sel) {
+          // reward code of iteration j+1 for the four sites at once: SigmaN (cooperators summed over
+          // the site's five groups, 0..25) << 3 | C_old << 2 | coop << 1 | state
+          const uint32_t *Nw32 = reinterpret_cast<const uint32_t *>(s_N + base);
+          const uint32_t snw = Nq + Nw32[-W] + Nw32[W] + __funnelshift_l(Nw32[-1], Nq, 8) +
+                               __funnelshift_r(Nq, Nw32[1], 8);
+          const uint32_t codew = (snw << 3) | (Cq << 2) | (coopw << 1) | sw;
+          if constexpr (FULL) {
+            // own cells, the periodic column image of the first / last quad of a row, and - for rows
+            // within two of a block edge - the neighbour block's ghost rows (DSMEM)
+            auto putw = [&](unsigned char *basep, int at) {
+              *reinterpret_cast<uint32_t *>(basep + o_code_n + at) = codew;
+              *reinterpret_cast<uint32_t *>(basep + o_R_n + at) = rneww;
+              *reinterpret_cast<uint32_t *>(basep + o_C_n + at) = coopw;
+              if (qc == 0) {
+                *reinterpret_cast<uint32_t *>(basep + o_code_n + at + L) = codew;
+                *reinterpret_cast<uint32_t *>(basep + o_R_n + at + L) = rneww;
+                *reinterpret_cast<uint32_t *>(basep + o_C_n + at + L) = coopw;
+              }
+              if (qc == QR - 1) {
+                *reinterpret_cast<uint32_t *>(basep + o_code_n + at - L) = codew;
+                *reinterpret_cast<uint32_t *>(basep + o_R_n + at - L) = rneww;
+                *reinterpret_cast<uint32_t *>(basep + o_C_n + at - L) = coopw;
+              }
+            };
+            putw(smem, base);
+            if (rr < 2) putw(smem_up, (nrow_up + rr + 2) * pitch + RG + 4 * qc);
+            if (rr >= nrow - 2) putw(smem_dn, (rr - nrow + 2) * pitch + RG + 4 * qc);
+          } else {
+            // L not a multiple of 4: the ghost columns share words with sites, store bytes
+            for (int k = 0; k < nvalid; ++k) {
+              const int col = 4 * qc + k;
+              const uint8_t cnew = (uint8_t)(codew >> (8 * k)), rnew = (uint8_t)(rneww >> (8 * k)),
+                            Cnew = (uint8_t)(coopw >> (8 * k));
+              const int gdx = (col < GC) ? L : ((col >= L - GC) ? -L : 0);
+              auto put = [&](unsigned char *basep, int at) {
+                basep[o_code_n + at] = cnew; basep[o_R_n + at] = rnew; basep[o_C_n + at] = Cnew;
+                if (gdx) {
+                  basep[o_code_n + at + gdx] = cnew; basep[o_R_n + at + gdx] = rnew; basep[o_C_n + at + gdx] = Cnew;
+                }
+              };
+              put(smem, base + k);
+              if (rr < 2) put(smem_up, (nrow_up + rr + 2) * pitch + RG + col);
+              if (rr >= nrow - 2) put(smem_dn, (rr - nrow + 2) * pitch + RG + col);
+            }
+          }
+        }
+        if constexpr (upd) {
 #pragma unroll
           for (int z = 0; z < 4; ++z) sQ[z * q_plane + qi] = make_float4(qv[z][0], qv[z][1], qv[z][2], qv[z][3]);
         }
         rr += q_dr; qc += q_dc;
         if (qc >= QR) { qc -= QR; rr += 1; }
       }
-    }
+    };
+    if (upd && sel) phase3(std::true_type{}, std::true_type{});
+    else if (upd) phase3(std::true_type{}, std::false_type{});
+    else if (sel) phase3(std::false_type{}, std::true_type{});
+    else phase3(std::false_type{}, std::false_type{});
 
     // ---- block statistics: exact integers through redux + shared atomics, fp32 sums per warp
     {
