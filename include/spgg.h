@@ -143,7 +143,9 @@ int spgg_set_replay(spgg_t *h, int n_steps, const double *u, const uint8_t *b);
 int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const double *u, const uint8_t *b);
 
 /* Run n_steps iterations of the loop body spgg.py:368-592 for all replicas
- * (asynchronous on `cuda_stream`, a cudaStream_t or NULL). */
+ * (asynchronous on `cuda_stream`, a cudaStream_t or NULL).  One launch for the
+ * whole call when the lattices fit in shared memory (one thread-block cluster
+ * per replica, csrc/spgg_resident.cuh), two launches per iteration otherwise. */
 int spgg_step(spgg_t *h, int n_steps, void *cuda_stream);
 int spgg_sync(spgg_t *h);
 

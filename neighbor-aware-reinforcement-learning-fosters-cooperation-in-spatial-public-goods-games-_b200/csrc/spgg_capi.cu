@@ -233,10 +233,10 @@ static res_fn_t pick_res2(int M, int action) {
 static res_fn_t pick_res(int M, int action, int L) {
   return (L % 4 == 0) ? pick_res2<true>(M, action) : pick_res2<false>(M, action);
 }
-// geometry of the cluster decomposition, or CS = 0 when the lattice does not fit on chip
-static ResGeom resident_geom(int L, size_t smem_limit) {
+// geometry of the decomposition into `cs` row blocks, or CS = 0 when a block does not fit on chip
+static ResGeom resident_geom(int L, int cs, size_t smem_limit) {
   ResGeom rg{};
-  const int cs = (L >= 2 * RES_CS_MAX) ? RES_CS_MAX : 1;
+  if (L < 2 * cs) cs = 1;  // a block needs two rows: its ghost rows come from the adjacent blocks only
   rg.rows_max = (L + cs - 1) / cs;
   rg.prow = rg.rows_max + 4;
   rg.QR = (L + 3) / 4;
@@ -378,16 +378,39 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   {
     cudaDeviceProp prop0;
     CUDA_TRY(cudaGetDeviceProperties(&prop0, device));
+    res_fn_t rf = pick_res(h->M, h->action, h->g.L);
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, pick_res(h->M, h->action, h->g.L)));
-    const ResGeom rg = resident_geom(g.L, prop0.sharedMemPerBlockOptin - fa.sharedSizeBytes - 1024);
-    h->resident = (h->mode == MODE_F32_I8) && g.wrap_rows && p0.row0 == 0 && rg.CS > 0 &&
-                  p0.algorithm == SPGG_ALGO_QLEARNING && getenv("SPGG_NO_RESIDENT") == nullptr;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, rf));
+    const size_t lim = prop0.sharedMemPerBlockOptin - fa.sharedSizeBytes - 1024;
+    const bool eligible = (h->mode == MODE_F32_I8) && g.wrap_rows && p0.row0 == 0 &&
+                          p0.algorithm == SPGG_ALGO_QLEARNING && getenv("SPGG_NO_RESIDENT") == nullptr;
+    // clusters of 8 CTAs (15 co-resident on a B200) serve batches best; a lattice that is alone (or
+    // nearly) on the GPU, or too large for 8 blocks, is spread over a non-portable cluster of 16
+    ResGeom rg = resident_geom(g.L, 8, lim);
+    if (eligible && g.L >= 32 && (rg.CS == 0 || n_replicas <= 4) && getenv("SPGG_RES_CS8") == nullptr) {
+      const ResGeom rg16 = resident_geom(g.L, 16, lim);
+      if (rg16.CS == 16 &&
+          cudaFuncSetAttribute(rf, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16u * (unsigned)n_replicas);
+        cfg.blockDim = dim3((unsigned)rg16.threads);
+        cfg.dynamicSmemBytes = ResSmem(rg16).total;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, rf, &cfg) == cudaSuccess && n_clusters >= 1) rg = rg16;
+      }
+      (void)cudaGetLastError();  // a refused opt-in leaves the portable geometry in place
+    }
+    h->resident = eligible && rg.CS > 0;
     if (h->resident) {
       h->rgeo = rg;
       h->smem_res = ResSmem(rg).total;
-      CUDA_TRY(cudaFuncSetAttribute(pick_res(h->M, h->action, h->g.L), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)h->smem_res));
+      // the opt-in is per function, not per handle: always the largest size any geometry may ask for
+      CUDA_TRY(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
     }
   }
   g.TR = h->fast ? FTR : (g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4));

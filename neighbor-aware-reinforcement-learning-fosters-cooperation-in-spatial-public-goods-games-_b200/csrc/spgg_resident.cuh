@@ -28,7 +28,7 @@ namespace spgg {
 namespace cg = cooperative_groups;
 
 constexpr int RES_THREADS = 512;  // upper bound; small lattices launch fewer
-constexpr int RES_CS_MAX = 8;     // portable cluster size
+constexpr int RES_CS_MAX = 16;    // largest cluster (8 is the portable size, 16 needs the non-portable opt-in)
 constexpr int RG = 4;             // ghost columns (bytes) on each side of a shared-memory plane row
 constexpr int RES_NI = 18;        // integer statistics per thread
 constexpr int RES_NF = 10;        // fp32 statistics per thread

@@ -118,9 +118,12 @@ F32_CASES = [
 
 
 @pytest.mark.parametrize("name,p", F32_CASES, ids=[c[0] for c in F32_CASES])
-def test_fp32_philox_vs_oracle_bit_exact(name, p):
-    """Throughput instantiation (fp32 Q, int8/fp32 R, Philox) == its C restatement."""
+def test_fp32_philox_vs_oracle_bit_exact(monkeypatch, name, p):
+    """Throughput instantiation (fp32 Q, int8/fp32 R, Philox) == its C restatement.  Lattices
+    that fit on chip would run on the resident cluster kernel (tests/test_gpu_resident.py covers
+    it); here the per-iteration kernels are pinned: general kernel, or TMA fast path (fast_*)."""
     from oracle import c_oracle
+    monkeypatch.setenv("SPGG_NO_RESIDENT", "1")
     p = full_params(p)
     L, n = p["L"], 60
     rs = np.random.RandomState(3)
@@ -154,6 +157,7 @@ def test_fast_path_equals_general_path(monkeypatch, second, state):
     Q0 = rs.uniform(-0.01, 0.01, (L, L, 2, 2))
     S0 = rs.randint(0, 2, (L, L))
     outs = []
+    monkeypatch.setenv("SPGG_NO_RESIDENT", "1")
     for no_fast in (False, True):
         if no_fast:
             monkeypatch.setenv("SPGG_NO_FAST", "1")
@@ -192,9 +196,12 @@ def test_fp32_replay_draws_vs_oracle():
     eng.close()
 
 
-def test_chunking_is_invisible():
+@pytest.mark.parametrize("path", ["resident", "per_iteration"])
+def test_chunking_is_invisible(monkeypatch, path):
     """step(7)+step(13) == step(20): the counter-based stream and the skewed pipeline do not
     depend on where the host cuts the run."""
+    if path == "per_iteration":
+        monkeypatch.setenv("SPGG_NO_RESIDENT", "1")
     L = 160
     p = full_params(dict(C1, L=L, use_second_order=True))
     rs = np.random.RandomState(9)
@@ -216,8 +223,9 @@ def test_chunking_is_invisible():
             assert np.array_equal(a, b)
 
 
-def test_batched_replicas_equal_single_runs():
+def test_batched_replicas_equal_single_runs(monkeypatch):
     """Replicas batched in one launch (the sweep of runner.py:117-156) == separate runs."""
+    monkeypatch.setenv("SPGG_NO_RESIDENT", "1")   # the general kernel's batching; resident: test_gpu_resident.py
     L, n = 100, 30
     plist = [full_params(dict(C1, L=L, r=r, influence_factor=k))
              for r, k in ((3.0, 1.0), (3.6, 0.0), (5.0, 2.0), (1.0, 0.5))]
@@ -238,9 +246,10 @@ def test_batched_replicas_equal_single_runs():
     eng.close()
 
 
-def test_batched_replicas_on_the_fast_path_equal_single_runs():
+def test_batched_replicas_on_the_fast_path_equal_single_runs(monkeypatch):
     """Same as above on 128-aligned lattices (TMA fast path, grid = replicas x CTAs, per-replica
     reward tables, Philox keys and early-exit flags)."""
+    monkeypatch.setenv("SPGG_NO_RESIDENT", "1")
     L, n = 256, 40
     plist = [full_params(dict(C1, L=L, r=r, influence_factor=k, reward_weight_payoff=w))
              for r, k, w in ((3.0, 1.0, 0.95), (4.0, 0.0, 1.0), (5.0, 2.0, 0.9))]

@@ -32,8 +32,36 @@ CASES = [
     ("act_m1_L102", dict(C2, L=102, use_second_order=False, r=3.0)),    # L % 4 != 0: partial last quad
     ("rep_m1_L17", dict(C1, L=17, rep_gain_C=0.5)),                     # odd side, blocks of 2-3 rows, half units
     ("rep_m2_L128", dict(C1, L=128, use_second_order=True, influence_factor=0.5)),
-    ("rep_m1_L240", dict(C1, L=240, reward_weight_payoff=0.9)),         # near the shared-memory limit
+    ("rep_m1_L240", dict(C1, L=240, reward_weight_payoff=0.9)),         # near the shared-memory limit of 8 blocks
+    ("act_m2_L256", dict(C2, L=256)),                                   # only fits as 16 blocks
+    ("rep_m2_L340", dict(C1, L=340, use_second_order=True)),            # 16 blocks of 21-22 rows, near the limit
 ]
+
+
+def test_cluster_of_8_equals_cluster_of_16(monkeypatch):
+    """A lone lattice is spread over a (non-portable) cluster of 16 CTAs, batches use clusters
+    of 8: the decomposition must be invisible (statistics rows included: integer columns
+    exact, fp32 sums grouped differently)."""
+    L, n = 200, 40
+    p = full_params(dict(C1, L=L, use_second_order=True))
+    S0, Q0 = _init(L, 23)
+    outs = []
+    for cs8 in (False, True):
+        if cs8:
+            monkeypatch.setenv("SPGG_RES_CS8", "1")
+        else:
+            monkeypatch.delenv("SPGG_RES_CS8", raising=False)
+        eng = _engine(p, seeds=5, precision="fp32")
+        eng.set_state(S0, np.zeros((L, L)), Q0)
+        eng.step(n)
+        outs.append(eng.get_state() + (eng.stats(),))
+        eng.close()
+    for a, b in zip(*outs):
+        if a.ndim == 2 and a.shape[1] == 40:
+            assert np.array_equal(a[:, EXACT], b[:, EXACT])
+            np.testing.assert_allclose(a[:, 18:31], b[:, 18:31], rtol=1e-5, atol=1e-4)
+        else:
+            assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("name,p", CASES, ids=[c[0] for c in CASES])
@@ -113,7 +141,11 @@ def test_resident_many_replicas_more_clusters_than_fit():
         single.step(n)
         for a, b in zip(eng.get_state(i), single.get_state()):
             assert np.array_equal(a, b)
-        assert np.array_equal(eng.stats(i), single.stats())
+        # the lone lattice runs on a cluster of 16, the batch on clusters of 8: integer columns
+        # exact, fp32 partial sums grouped differently
+        ra, rb = eng.stats(i), single.stats()
+        assert np.array_equal(ra[:, EXACT], rb[:, EXACT])
+        np.testing.assert_allclose(ra[:, 18:31], rb[:, 18:31], rtol=1e-5, atol=1e-4)
         single.close()
     eng.close()
 
