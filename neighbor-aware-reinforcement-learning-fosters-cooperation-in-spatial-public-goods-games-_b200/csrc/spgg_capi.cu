@@ -846,6 +846,24 @@ static int resident_chunk(spgg_handle *h, int n_steps, cudaStream_t st) {
   a.t0 = (int)h->pend_t0;
   a.n_steps = n_steps;
   a.cap = h->cap;
+#ifdef SPGG_RES_TRACE
+  {  // debug builds only: print the per-phase cycle sums of the previous resident launch
+    static long long *d_tr = nullptr;
+    const int n_cta = h->rgeo.CS * h->n_rep;
+    if (!d_tr) { cudaMalloc(&d_tr, sizeof(long long) * 8 * 4096); cudaMemset(d_tr, 0, sizeof(long long) * 8 * 4096); }
+    else if (getenv("SPGG_RES_TRACE_PRINT")) {
+      std::vector<long long> t(8 * (size_t)n_cta);
+      cudaDeviceSynchronize();
+      cudaMemcpy(t.data(), d_tr, t.size() * 8, cudaMemcpyDeviceToHost);
+      for (int c = 0; c < std::min(n_cta, 16); ++c) {
+        fprintf(stderr, "res_trace cta %2d:", c);
+        for (int z = 0; z < 7; ++z) fprintf(stderr, " %10lld", t[(size_t)c * 8 + z]);
+        fprintf(stderr, "\n");
+      }
+    }
+    a.trace = d_tr;
+  }
+#endif
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(h->rgeo.CS * h->n_rep));
   cfg.blockDim = dim3((unsigned)h->rgeo.threads);
@@ -859,7 +877,12 @@ static int resident_chunk(spgg_handle *h, int n_steps, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res(h->M, h->action, h->g.L), a));
-  h->launches += 1;
+  {  // raw statistics rows -> public layout
+    const int n_rows = n_steps + 1, total = n_rows * h->n_rep;
+    k_resident_rows<<<(total + 127) / 128, 128, 0, st>>>(h->d_rc, h->d_stats, h->n_rep, h->cap, n_rows);
+    CUDA_TRY(cudaGetLastError());
+  }
+  h->launches += 2;
   h->pend_rel = n_steps;
   h->pend_resident = true;
   return SPGG_OK;

@@ -27,12 +27,30 @@
 namespace spgg {
 namespace cg = cooperative_groups;
 
+// debug builds only (-DSPGG_RES_TRACE): cycle stamps of one thread at the phase boundaries of every
+// iteration, accumulated per phase into RArgs::trace[rank][8]
+#ifdef SPGG_RES_TRACE
+#define RES_STAMP(slot)                                                     \
+  do {                                                                      \
+    if (tid == 0) {                                                         \
+      const long long now_ = clock64();                                     \
+      trace_acc[slot] += now_ - trace_t;                                    \
+      trace_t = now_;                                                       \
+    }                                                                       \
+  } while (0)
+#else
+#define RES_STAMP(slot) do {} while (0)
+#endif
+
 constexpr int RES_THREADS = 512;  // upper bound; small lattices launch fewer
 constexpr int RES_CS_MAX = 16;    // largest cluster (8 is the portable size, 16 needs the non-portable opt-in)
 constexpr int RG = 4;             // ghost columns (bytes) on each side of a shared-memory plane row
 constexpr int RES_NI = 18;        // integer statistics per thread
 constexpr int RES_NF = 10;        // fp32 statistics per thread
 constexpr int RES_NRED = RES_NI + RES_NF;
+constexpr int RES_RAW = RES_NRED + 1;  // raw statistics row: the 28 lattice sums + the global max
+constexpr int RES_RING = 16;           // raw rows kept on chip between flushes to HBM
+constexpr int RES_RAW_GMAX = 39;       // column of a raw row in HBM that carries the global max
 
 struct ResGeom {
   int CS;        // CTAs per cluster = row blocks per replica
@@ -46,7 +64,7 @@ struct ResGeom {
 // byte offsets of the per-CTA shared-memory planes (identical in every CTA of a cluster, so a
 // local offset is valid in a neighbour's window)
 struct ResSmem {
-  size_t q, val, code[2], R[2], C[2], N, tab, redf, redi, gmx, nsel, part, total;
+  size_t q, val, code[2], R[2], C[2], N, tab, redf, redi, gmx, nsel, part, ring, total;
   __host__ __device__ explicit ResSmem(const ResGeom &rg) {
     const size_t nq = (size_t)rg.rows_max * rg.QR * 16;  // one float4 plane (one Q entry, 4 sites per element)
     const size_t nb = (size_t)rg.prow * rg.pitch;
@@ -58,12 +76,13 @@ struct ResSmem {
     for (int i = 0; i < 2; ++i) { C[i] = o; o += nb; }
     N = o; o += nb;
     tab = o; o += 256 * sizeof(float);
-    redf = o; o += sizeof(float) * (RES_THREADS / 32) * RES_NF;
+    redf = o; o += sizeof(float) * (RES_THREADS / 32) * 32;
     redi = o; o += sizeof(unsigned) * (RES_NI + 2);
     gmx = o; o += sizeof(float) * RES_CS_MAX;
     nsel = o; o += sizeof(unsigned) * RES_CS_MAX;
     o = (o + 15) / 16 * 16;
-    part = o; o += sizeof(double) * RES_CS_MAX * RES_NRED;
+    part = o; o += 2 * sizeof(double) * RES_CS_MAX * RES_NRED;  // two buffers, by iteration parity
+    ring = o; o += sizeof(double) * RES_RING * RES_RAW;         // finished raw rows waiting for their flush (rank 0)
     total = (o + 15) / 16 * 16;
   }
 };
@@ -81,6 +100,9 @@ struct RArgs {
   int t0;             // iterations completed before this launch
   int n_steps;
   int cap;
+#ifdef SPGG_RES_TRACE
+  long long *trace;   // [n_rep * CS][8] accumulated cycles per phase
+#endif
 };
 
 // Rewards around a quad (4 consecutive sites of a row, first plane index `base`) held in
@@ -174,7 +196,6 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   const int o_code0 = (int)lay.code[0], o_R0 = (int)lay.R[0], o_C0 = (int)lay.C[0];
   const int nb = rg.prow * pitch;  // bytes per byte plane; set 1 follows set 0
   __shared__ RepConst s_rc;
-  __shared__ double s_fold[RES_NRED];
   __shared__ int s_noff[12];  // plane-index offset of neighbour z: dx*pitch + dy
   if (threadIdx.x < 12) s_noff[threadIdx.x] = c_off[threadIdx.x][0] * pitch + c_off[threadIdx.x][1];
 
@@ -229,8 +250,43 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   const int q_r0 = tid / QR, q_c0 = tid % QR, q_dr = nthr / QR, q_dc = nthr % QR;
   const long long n_sites = (long long)L * L;
 
+  // Raw statistics row of iteration fs (rank 0, warp 0): the 28 lattice sums (block rows folded in
+  // a fixed order) and the global max.  It is not on the critical path - the row of iteration s is
+  // folded inside the window of the NEXT iteration's max-exchange barrier (arrive - fold - wait),
+  // while the other blocks' arrivals are in flight - and it does not touch HBM: rows collect in a
+  // shared-memory ring that is flushed every RES_RING iterations (a cluster barrier waits for the
+  // thread's outstanding global stores).  k_resident_rows turns raw rows into the public layout.
+  double *s_ring = reinterpret_cast<double *>(smem + lay.ring);
+  int ring_first = -1, ring_last = -1;  // iterations of the rows waiting in the ring
+  auto flush_ring = [&]() {
+    if (ring_first < 0) return;
+    for (int r = ring_first; r <= ring_last; ++r) {
+      double *row = a.stats + ((long long)rep * a.cap + r) * NSTAT;
+      if (lane < RES_NRED) row[lane] = s_ring[(r % RES_RING) * RES_RAW + lane];
+      if (lane == RES_NRED) row[RES_RAW_GMAX] = s_ring[(r % RES_RING) * RES_RAW + RES_NRED];
+    }
+    ring_first = -1;
+  };
+  auto do_fold = [&](int fs, float fgm) {
+    double f = 0.0;
+    if (lane < RES_NRED)
+      for (int k = 0; k < CS; ++k) f += s_part[(fs & 1) * (RES_CS_MAX * RES_NRED) + k * RES_NRED + lane];
+    if (lane == RES_NRED) f = (double)fgm;
+    if (lane <= RES_NRED) s_ring[(fs % RES_RING) * RES_RAW + lane] = f;
+    if (ring_first < 0) ring_first = fs;
+    ring_last = fs;
+    __syncwarp();
+    if (fs - ring_first == RES_RING - 1) flush_ring();
+  };
+  int pend_s = -1;
+  float pend_gm = 0.0f;
+
   int stop = a.stop_at[rep];
   int cur = 0;
+#ifdef SPGG_RES_TRACE
+  long long trace_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long trace_t = clock64();
+#endif
   for (int s = 0; s <= a.n_steps; ++s) {
     const int j = a.t0 + s;
     if (stop >= 0 && j > stop) break;
@@ -271,6 +327,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       }
     }
     __syncthreads();
+    RES_STAMP(0);  // phase 1 + barrier
 
     // ---- phase 2: lattice-global max |reward difference| (spgg.py:486-488): each unordered
     // neighbour pair once, block max, all-to-all through DSMEM
@@ -300,11 +357,16 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
       if (lane == 0) atomicMax(&s_redi[RES_NI], wm);
       __syncthreads();
+      RES_STAMP(1);  // phase 2 + block max
       if (tid < CS) {
         float *dst = reinterpret_cast<float *>(cluster.map_shared_rank(smem, tid) + lay.gmx);
         dst[rank] = __uint_as_float(s_redi[RES_NI]);
       }
-      cluster.sync();
+      cluster.barrier_arrive();
+      if (rank == 0 && warp == 0 && pend_s >= 0) do_fold(pend_s, pend_gm);
+      pend_s = -1;
+      cluster.barrier_wait();
+      RES_STAMP(2);  // max exchange + cluster barrier A (+ the previous iteration's statistics row on rank 0)
       for (int k = 0; k < CS; ++k) gm = fmaxf(gm, s_gmx[k]);
       inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));  // spgg.py:489 denominator
     }
@@ -508,48 +570,52 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
     else if (sel) phase3(std::false_type{}, std::true_type{});
     else phase3(std::false_type{}, std::false_type{});
 
-    // ---- block statistics: exact integers through redux + shared atomics, fp32 sums per warp
+    RES_STAMP(3);  // phase 3
+    // ---- block statistics.  All 28 per-thread values travel as fp32 (the integer counters of a
+    // block stay below 2^24, so their fp32 sums are exact) through ONE transposing butterfly: at
+    // each of the five levels a lane keeps half of its values and hands the other half to its
+    // partner, so 31 shuffles reduce all values at once and lane z ends up with the warp sum of
+    // value z (a reduction per value would cost 28 x 5 dependent shuffles).
     {
-      unsigned iv[RES_NI];
+      float v[32];
 #pragma unroll
       for (int z = 0; z < 4; ++z) {
-        iv[z] = (pk_n >> (8 * z)) & 0xffu;
-        iv[4 + z] = (unsigned)((pk_sn >> (16 * z)) & 0xffffull);
+        v[z] = (float)((pk_n >> (8 * z)) & 0xffu);
+        v[4 + z] = (float)(unsigned)((pk_sn >> (16 * z)) & 0xffffull);
+        v[18 + z] = tq[z];
+        v[22 + z] = tqc[z];
+        v[28 + z] = 0.0f;
       }
 #pragma unroll
-      for (int z = 0; z < 6; ++z) iv[8 + z] = (unsigned)((pk_grp >> (10 * z)) & 0x3ffull);
-      iv[14] = n_best; iv[15] = n_best2; iv[16] = n_sel_coop; iv[17] = (unsigned)tri;
+      for (int z = 0; z < 6; ++z) v[8 + z] = (float)(unsigned)((pk_grp >> (10 * z)) & 0x3ffull);
+      v[14] = (float)n_best; v[15] = (float)n_best2; v[16] = (float)n_sel_coop; v[17] = (float)tri;
+      v[26] = tni; v[27] = tratio;
 #pragma unroll
-      for (int z = 0; z < RES_NI; ++z) {
-        const unsigned x = __reduce_add_sync(0xffffffffu, iv[z]);  // two's complement: exact for the signed sum too
-        if (lane == 0 && x) atomicAdd(&s_redi[z], x);
-      }
-      if (upd) {
-        const float fv[RES_NF] = {tq[0], tq[1], tq[2], tq[3], tqc[0], tqc[1], tqc[2], tqc[3], tni, tratio};
+      for (int lvl = 0; lvl < 5; ++lvl) {
+        const int o = 16 >> lvl, half = 16 >> lvl;  // partner distance; values kept at this level
+        const bool hi = (lane & o) != 0;
 #pragma unroll
-        for (int z = 0; z < RES_NF; ++z) {
-          float x = fv[z];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-          if (lane == 0) s_redf[warp * RES_NF + z] = x;
+        for (int i = 0; i < half; ++i) {
+          const float keep = hi ? v[i + half] : v[i];
+          const float send = hi ? v[i] : v[i + half];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
       }
+      if (lane < RES_NRED) s_redf[warp * 32 + lane] = v[0];
     }
     __syncthreads();
     if (tid < RES_NRED) {
       double x = 0.0;
-      if (tid < RES_NI) {
-        x = (tid == RES_NI - 1) ? (double)(int)s_redi[tid] : (double)s_redi[tid];
-      } else if (upd) {
-        for (int w = 0; w < nwarp; ++w) x += (double)s_redf[w * RES_NF + (tid - RES_NI)];
-      }
+      for (int w = 0; w < nwarp; ++w) x += (double)s_redf[w * 32 + tid];
       double *dst = reinterpret_cast<double *>(cluster.map_shared_rank(smem, 0) + lay.part);
-      dst[rank * RES_NRED + tid] = x;
-    } else if (tid >= 32 && tid < 32 + CS) {
-      unsigned *dst = reinterpret_cast<unsigned *>(cluster.map_shared_rank(smem, tid - 32) + lay.nsel);
-      dst[rank] = s_redi[16];
+      dst[(s & 1) * (RES_CS_MAX * RES_NRED) + rank * RES_NRED + tid] = x;
+      if (tid == 16)  // cooperating actions just chosen by this block: to every block (early-exit test)
+        for (int k = 0; k < CS; ++k)
+          reinterpret_cast<unsigned *>(cluster.map_shared_rank(smem, k) + lay.nsel)[rank] = (unsigned)x;
     }
+    RES_STAMP(4);  // reductions + block barrier + pushes
     cluster.sync();  // ghost rows, partial rows and counters of every block have landed
+    RES_STAMP(5);  // cluster barrier B
 
     if (sel) {
       // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405)
@@ -558,57 +624,23 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       if (tot == 0 || tot == n_sites) stop = j + 1;
       cur ^= 1;
     }
-    if (rank == 0 && warp == 0) {
-      // fold the block rows in a fixed order ...
-      if (lane < RES_NRED) {
-        double x = 0.0;
-        for (int k = 0; k < CS; ++k) x += s_part[k * RES_NRED + lane];
-        s_fold[lane] = x;
-      }
-      __syncwarp();
-    }
-    if (rank == 0 && tid == 0) {
-      // ... and finish the statistics row like k_step does
-      const double *f = s_fold;
-      double *row = a.stats + ((long long)rep * a.cap + s) * NSTAT;
-      row[ST_SUM_R] = f[17] * rc.rq;
-      if (upd) {
-        const double nc[4] = {f[0], f[1], f[2], f[3]};
-        double Pc[4];
-        for (int z = 0; z < 4; ++z) {  // exact-count payoff sums per class
-          const double C = (z >> 1) ? 1.0 : 0.0;
-          Pc[z] = ((rc.rc * f[4 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) / rc.span;
-        }
-        row[ST_NC_OLD] = nc[2] + nc[3];
-        row[ST_N_CD] = nc[2];
-        row[ST_N_DC] = nc[1];
-        row[ST_NC_NEW] = nc[1] + nc[3];
-        const double sumP = Pc[0] + Pc[1] + Pc[2] + Pc[3];
-        row[ST_SUM_P] = sumP;
-        row[ST_SUM_P_C] = Pc[2] + Pc[3];
-        row[ST_SUM_P_D] = Pc[0] + Pc[1];
-        row[ST_SUM_WP_P] = rc.wP * sumP;
-        row[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
-        row[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
-        row[ST_SUM_RATIO] = f[27];
-        for (int z = 0; z < 6; ++z) row[ST_GROUP0 + z] = f[8 + z];
-        for (int z = 0; z < 4; ++z) {
-          row[ST_SUM_Q + z] = f[18 + z];
-          row[ST_SUM_Q_C + z] = f[22 + z];
-          row[ST_SUM_Q_D + z] = f[18 + z] - f[22 + z];
-        }
-        row[ST_SUM_NI] = f[26];
-        row[ST_N_BEST_POS] = f[14];
-        row[ST_N_BEST_2ND] = f[15];
-        row[ST_GMAX] = (double)gm;
-      }
-    }
+    pend_s = s; pend_gm = gm;  // the row is folded inside the next barrier window
     if (tid <= RES_NI) s_redi[tid] = 0u;  // next use is behind the next block barrier
+    RES_STAMP(6);  // early-exit test, fold and statistics row (rank 0)
+  }
+
+  if (rank == 0 && warp == 0) {
+    if (pend_s >= 0) do_fold(pend_s, pend_gm);
+    flush_ring();
   }
 
   // ---- write the state back: Q, reputation, strategy bits (ghost cells included, so the
   // per-iteration kernels can continue from these planes)
   if (rank == 0 && tid == 0) a.stop_at[rep] = stop;
+#ifdef SPGG_RES_TRACE
+  if (tid == 0 && a.trace)
+    for (int z = 0; z < 8; ++z) a.trace[(long long)blockIdx.x * 8 + z] = trace_acc[z];
+#endif
   {
     const uint8_t *Rc = smem + o_R0 + cur * nb;
     const uint8_t *Cc = smem + o_C0 + cur * nb;
@@ -629,6 +661,56 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       store_bits_word(Sg, g, row_start + rr, wi, word);
     }
   }
+}
+
+// Raw statistics rows of a resident chunk -> the public row layout (include/spgg.h), with the row
+// arithmetic of k_step's fold.  One thread per row; row 0 of a chunk belongs to the select-only
+// first trip and carries only the reputation sum.
+__global__ void k_resident_rows(const RepConst *rcs, double *stats, int n_rep, int cap, int n_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rep * n_rows) return;
+  const int rep = i / n_rows, r = i - rep * n_rows;
+  const RepConst &rc = rcs[rep];
+  double *row = stats + ((long long)rep * cap + r) * NSTAT;
+  double f[RES_NRED];
+#pragma unroll
+  for (int z = 0; z < RES_NRED; ++z) f[z] = row[z];
+  const double gm = row[RES_RAW_GMAX];
+  double s[NSTAT];
+#pragma unroll
+  for (int z = 0; z < NSTAT; ++z) s[z] = 0.0;
+  s[ST_SUM_R] = f[17] * rc.rq;
+  if (r > 0) {
+    const double nc[4] = {f[0], f[1], f[2], f[3]};
+    double Pc[4];
+    for (int z = 0; z < 4; ++z) {  // exact-count payoff sums per class: P = ((rc*SN/5 - 5*cost*C) - lo)/span
+      const double C = (z >> 1) ? 1.0 : 0.0;
+      Pc[z] = ((rc.rc * f[4 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) / rc.span;
+    }
+    s[ST_NC_OLD] = nc[2] + nc[3];
+    s[ST_N_CD] = nc[2];
+    s[ST_N_DC] = nc[1];
+    s[ST_NC_NEW] = nc[1] + nc[3];
+    s[ST_SUM_P] = Pc[0] + Pc[1] + Pc[2] + Pc[3];
+    s[ST_SUM_P_C] = Pc[2] + Pc[3];
+    s[ST_SUM_P_D] = Pc[0] + Pc[1];
+    s[ST_SUM_WP_P] = rc.wP * s[ST_SUM_P];
+    s[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
+    s[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
+    s[ST_SUM_RATIO] = f[27];
+    for (int z = 0; z < 6; ++z) s[ST_GROUP0 + z] = f[8 + z];
+    for (int z = 0; z < 4; ++z) {
+      s[ST_SUM_Q + z] = f[18 + z];
+      s[ST_SUM_Q_C + z] = f[22 + z];
+      s[ST_SUM_Q_D + z] = f[18 + z] - f[22 + z];
+    }
+    s[ST_SUM_NI] = f[26];
+    s[ST_N_BEST_POS] = f[14];
+    s[ST_N_BEST_2ND] = f[15];
+    s[ST_GMAX] = gm;
+  }
+#pragma unroll
+  for (int z = 0; z < NSTAT; ++z) row[z] = s[z];
 }
 
 }  // namespace spgg
