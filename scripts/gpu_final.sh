@@ -14,6 +14,6 @@ echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 5 
 echo "== ncu k_step"; bash scripts/gpu_profile.sh $TAG > gpurun_out/profile_$TAG.log 2>&1; tail -3 gpurun_out/profile_$TAG.log
 echo "== ncu resident"
 RCMD="python bench.py --workload sweep --steps 1 --warmup 1 --inner 300"
-$RCMD > gpurun_out/plain_res_${TAG}.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_res_${TAG}.csv $RCMD > gpurun_out/ncu_list_res_${TAG}.log 2>&1; echo "list rc=$?"
+$RCMD > gpurun_out/plain_res_${TAG}.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_res_${TAG}.csv $RCMD > gpurun_out/ncu_list_res_${TAG}.log 2>&1; echo "list rc=$?"
 $RCMD > gpurun_out/plain2_res_${TAG}.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_resident -s 2 -c 1 -o gpurun_out/prof_res_${TAG} -f $RCMD > gpurun_out/ncu_full_res_${TAG}.log 2>&1; echo "full rc=$?"
 ls gpurun_out | wc -l
