@@ -55,10 +55,33 @@ def _object_header(messages) -> bytes:
     return struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body
 
 
+class _OnDisk:
+    """A dataset already streamed to the file (large arrays are not kept in memory)."""
+
+    def __init__(self, path, addr, shape, dtype):
+        self.path, self.addr, self.shape, self.dtype = path, addr, tuple(shape), np.dtype(dtype)
+
+    def load(self):
+        n = int(np.prod(self.shape)) if self.shape else 1
+        return np.fromfile(self.path, dtype=self.dtype, count=n, offset=self.addr).reshape(self.shape)
+
+
 class _Writer:
+    """Streams every dataset's bytes to the file when it is created (like h5py does - a 16.7 M-site
+    lattice snapshot is written once, straight from the array's buffer) and appends the metadata
+    (root header, B-tree, heap, symbol node, dataset headers) behind the data on ``close``; the
+    superblock at offset 0 is written last.  Addresses in HDF5 are arbitrary, so readers do not care
+    where the metadata lives."""
+
+    KEEP_BYTES = 1 << 20   # smaller arrays stay readable through ``File[name]`` without touching the disk
+
     def __init__(self, path):
         self.path = path
         self.datasets = {}
+        self._meta = {}       # name -> (data address or UNDEF, shape, dtype, nbytes)
+        self._f = open(path, "wb")
+        self._f.write(b"\0" * 96)   # superblock placeholder
+        self._pos = 96
 
     def create_dataset(self, name, data=None, **_ignored):
         arr = np.asarray(data)
@@ -70,11 +93,27 @@ class _Writer:
             arr = arr.astype(np.float64)
         if name in self.datasets:
             raise ValueError(f"Unable to create dataset (name already exists): {name}")
-        self.datasets[name] = np.ascontiguousarray(arr.astype(arr.dtype.newbyteorder("<")))
+        _dtype_message(arr.dtype)    # unsupported dtypes fail here, before anything is written
+        arr = np.ascontiguousarray(arr, dtype=arr.dtype.newbyteorder("<"))
+        addr = UNDEF
+        if arr.nbytes:
+            pad = (-self._pos) % 8
+            if pad:
+                self._f.write(b"\0" * pad)
+                self._pos += pad
+            addr = self._pos
+            self._f.write(memoryview(arr.reshape(-1)).cast("B"))
+            self._pos += arr.nbytes
+        self._meta[name] = (addr, arr.shape, arr.dtype, arr.nbytes)
+        self.datasets[name] = arr.copy() if arr.nbytes <= self.KEEP_BYTES else _OnDisk(self.path, addr, arr.shape, arr.dtype)
+        if isinstance(self.datasets[name], _OnDisk):
+            self._f.flush()
         return self.datasets[name]
 
     def close(self):
-        names = sorted(self.datasets, key=lambda s: s.encode())  # strcmp order
+        if self._f is None:
+            return
+        names = sorted(self._meta, key=lambda s: s.encode())  # strcmp order
         n = len(names)
         leaf_k = max(4, (n + 1) // 2)          # one SNOD holds 2*leaf_k symbols
         internal_k = 16
@@ -85,10 +124,10 @@ class _Writer:
             name_off[nm] = len(heap)
             heap += _pad8(nm.encode() + b"\0")
         heap_data = bytes(heap)
-        # ---- layout of the file
-        off_super = 0
-        off_root_hdr = 96
-        root_hdr = _object_header([_message(0x0011, struct.pack("<QQ", 0, 0))])  # patched below
+        # ---- layout of the metadata block, behind the data
+        meta0 = self._pos + ((-self._pos) % 8)
+        off_root_hdr = meta0
+        root_hdr = _object_header([_message(0x0011, struct.pack("<QQ", 0, 0))])  # size only; emitted below
         off_btree = off_root_hdr + len(root_hdr)
         btree_size = 24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8
         off_heap = off_btree + btree_size
@@ -97,38 +136,24 @@ class _Writer:
         off_snod = off_heap_data + len(heap_data)
         snod_size = 8 + 2 * leaf_k * 40
         pos = off_snod + snod_size
-        hdr_addr, data_addr, headers = {}, {}, {}
+        hdr_addr, headers = {}, {}
         for nm in names:
-            arr = self.datasets[nm]
-            dims = arr.shape
+            addr, dims, dt, nbytes = self._meta[nm]
             space = struct.pack("<BBB5x", 1, len(dims), 0) + b"".join(struct.pack("<Q", d) for d in dims)
             fill = struct.pack("<BBBB", 2, 2, 2, 0)   # v2: late allocation, write if set, undefined
-            hdr_addr[nm] = pos
-            # layout address is patched once the header size is known
-            hdr_len = len(_object_header([
-                _message(0x0001, space), _message(0x0003, _dtype_message(arr.dtype), 1),
-                _message(0x0005, fill, 1), _message(0x0008, struct.pack("<BBQQ", 3, 1, 0, 0))]))
-            daddr = pos + hdr_len
-            daddr += (-daddr) % 8
-            nbytes = arr.nbytes
-            layout = struct.pack("<BBQQ", 3, 1, daddr if nbytes else UNDEF, nbytes)
+            layout = struct.pack("<BBQQ", 3, 1, addr if nbytes else UNDEF, nbytes)
             headers[nm] = _object_header([
-                _message(0x0001, space), _message(0x0003, _dtype_message(arr.dtype), 1),
+                _message(0x0001, space), _message(0x0003, _dtype_message(dt), 1),
                 _message(0x0005, fill, 1), _message(0x0008, layout)])
-            data_addr[nm] = daddr
-            pos = daddr + nbytes
+            hdr_addr[nm] = pos
+            pos += len(headers[nm])
             pos += (-pos) % 8
         eof = pos
-        # ---- emit
-        out = bytearray(eof)
-        sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, leaf_k, internal_k, 0)
-        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
-        # root symbol table entry: name offset, header address, cache type 1, reserved, scratch
-        sb += struct.pack("<QQII", 0, off_root_hdr, 1, 0) + struct.pack("<QQ", off_btree, off_heap)
-        assert len(sb) == 96
-        out[off_super:off_super + 96] = sb
-        root_hdr = _object_header([_message(0x0011, struct.pack("<QQ", off_btree, off_heap))])
-        out[off_root_hdr:off_root_hdr + len(root_hdr)] = root_hdr
+        # ---- emit the metadata block
+        out = bytearray(eof - meta0)
+        def put(addr, b):
+            out[addr - meta0:addr - meta0 + len(b)] = b
+        put(off_root_hdr, _object_header([_message(0x0011, struct.pack("<QQ", off_btree, off_heap))]))
         # B-tree node: group node, level 0, one child (the SNOD) when there are symbols
         used = 1 if n else 0
         bt = b"TREE" + struct.pack("<BBHQQ", 0, 0, used, UNDEF, UNDEF)
@@ -137,24 +162,29 @@ class _Writer:
             keys_children += struct.pack("<QQ", off_snod, name_off[names[-1]])
         bt += keys_children
         bt += b"\0" * (btree_size - len(bt))
-        out[off_btree:off_btree + btree_size] = bt
+        put(off_btree, bt)
         # local heap header: no free blocks (free-list head = 1 == H5HL_FREE_NULL)
-        hh = b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), 1, off_heap_data)
-        out[off_heap:off_heap + heap_hdr_size] = hh
-        out[off_heap_data:off_heap_data + len(heap_data)] = heap_data
+        put(off_heap, b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), 1, off_heap_data))
+        put(off_heap_data, heap_data)
         sn = b"SNOD" + struct.pack("<BBH", 1, 0, n)
         for nm in names:
             sn += struct.pack("<QQII16x", name_off[nm], hdr_addr[nm], 0, 0)
         sn += b"\0" * (snod_size - len(sn))
-        out[off_snod:off_snod + snod_size] = sn
+        put(off_snod, sn)
         for nm in names:
-            h = headers[nm]
-            out[hdr_addr[nm]:hdr_addr[nm] + len(h)] = h
-            arr = self.datasets[nm]
-            if arr.nbytes:
-                out[data_addr[nm]:data_addr[nm] + arr.nbytes] = arr.tobytes()
-        with open(self.path, "wb") as f:
-            f.write(bytes(out))
+            put(hdr_addr[nm], headers[nm])
+        self._f.write(b"\0" * (meta0 - self._pos))
+        self._f.write(bytes(out))
+        # ---- superblock (version 0) and the root symbol-table entry: name offset, header address,
+        # cache type 1, reserved, scratch = B-tree and heap addresses
+        sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, leaf_k, internal_k, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+        sb += struct.pack("<QQII", 0, off_root_hdr, 1, 0) + struct.pack("<QQ", off_btree, off_heap)
+        assert len(sb) == 96
+        self._f.seek(0)
+        self._f.write(sb)
+        self._f.close()
+        self._f = None
 
 
 class _Dataset:
@@ -262,7 +292,8 @@ class File:
 
     def __getitem__(self, name):
         src = self._w.datasets if self._w is not None else self._data
-        return _Dataset(src[name])
+        d = src[name]
+        return _Dataset(d.load() if isinstance(d, _OnDisk) else d)
 
     def close(self):
         if self._w is not None:
