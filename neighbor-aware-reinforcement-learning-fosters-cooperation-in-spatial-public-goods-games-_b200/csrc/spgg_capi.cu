@@ -242,7 +242,9 @@ static ResGeom resident_geom(int L, int cs, size_t smem_limit) {
   rg.QR = (L + 3) / 4;
   rg.pitch = (RG + rg.QR * 4 + RG + 15) / 16 * 16;
   const int quads = rg.rows_max * rg.QR;
-  rg.threads = std::max(64, std::min(RES_THREADS, (quads + 31) / 32 * 32));
+  int max_thr = RES_THREADS;
+  if (const char *e = getenv("SPGG_RES_THREADS")) max_thr = std::max(64, std::min(RES_THREADS, atoi(e) / 32 * 32));  // tuning experiments
+  rg.threads = std::max(64, std::min(max_thr, (quads + 31) / 32 * 32));
   rg.CS = (ResSmem(rg).total <= smem_limit) ? cs : 0;
   return rg;
 }
@@ -387,7 +389,8 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     // clusters of 8 CTAs (15 co-resident on a B200) serve batches best; a lattice that is alone (or
     // nearly) on the GPU, or too large for 8 blocks, is spread over a non-portable cluster of 16
     ResGeom rg = resident_geom(g.L, 8, lim);
-    if (eligible && g.L >= 32 && (rg.CS == 0 || n_replicas <= 4) && getenv("SPGG_RES_CS8") == nullptr) {
+    if (eligible && g.L >= 32 && (rg.CS == 0 || n_replicas <= 4 || getenv("SPGG_RES_CS16") != nullptr) &&
+        getenv("SPGG_RES_CS8") == nullptr) {
       const ResGeom rg16 = resident_geom(g.L, 16, lim);
       if (rg16.CS == 16 &&
           cudaFuncSetAttribute(rf, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
