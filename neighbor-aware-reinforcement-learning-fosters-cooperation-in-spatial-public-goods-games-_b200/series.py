@@ -18,11 +18,31 @@ def _safe_div(num, den, empty):
 
 
 def epsilon_after(eps0: float, decay: float, eps_min: float, n: int) -> np.ndarray:
-    """epsilon recorded after each of n iterations (algorithms.py:40-42, spgg.py:548-550)."""
+    """epsilon recorded after each of n iterations (algorithms.py:40-42, spgg.py:548-550):
+    e <- max(e * decay, eps_min), iterated.  For a non-increasing sequence (0 <= decay <= 1,
+    eps0 >= eps_min) this is the running left-to-right product clamped from below - the same
+    sequence of roundings, without a Python loop per iteration."""
+    n = int(n)
+    if n <= 0:
+        return np.empty(0)
+    e0, d, m = float(eps0), float(decay), float(eps_min)
+    if 0.0 <= d <= 1.0 and e0 >= m >= 0.0:
+        out = np.empty(n + 1)
+        out[0] = e0
+        out[1:] = d
+        np.multiply.accumulate(out, out=out)       # ((e0*d)*d)*d ... sequentially
+        below = np.nonzero(out[1:] < m)[0]
+        if below.size == 0:
+            return out[1:].copy()
+        k = int(below[0])                          # first clamped entry; once at eps_min it stays there
+        if m * d <= m:
+            res = out[1:].copy()
+            res[k:] = m
+            return res
     out = np.empty(n)
-    e = float(eps0)
+    e = e0
     for t in range(n):
-        e = max(e * decay, eps_min)
+        e = max(e * d, m)
         out[t] = e
     return out
 

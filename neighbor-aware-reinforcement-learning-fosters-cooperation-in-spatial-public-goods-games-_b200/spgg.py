@@ -135,15 +135,23 @@ class SPGG:
                 "built into the fused CUDA step (the reference's four rules are); "
                 "there is no CPU fallback")
 
-    def _snapshot(self, eng, i, data_file, snaps, replica=0):
-        """State before iteration i acts (spgg.py:397-402)."""
+    def _snapshot(self, eng, i, data_file, snaps, replica=0, deferred=None):
+        """State before iteration i acts (spgg.py:397-402).  The device->host copy happens now;
+        with ``deferred`` (a list) the histogram and the HDF5 writes are queued so the caller can
+        run them while the GPU works on the next chunk."""
         S, R, _ = eng.get_state(replica, want_q=False)
-        data_file.create_dataset(f"R_snapshot_{i}", data=R)
-        rep_hist, rep_bins = np.histogram(R, bins=20, range=(self.R_min, self.R_max))
-        data_file.create_dataset(f"rep_hist_{i}", data=rep_hist)
-        data_file.create_dataset(f"rep_bins_{i}", data=rep_bins)
-        data_file.create_dataset(f"Sn_snapshot_{i}", data=S.astype(np.int64))
         snaps[i] = True
+
+        def write():
+            data_file.create_dataset(f"R_snapshot_{i}", data=R)
+            rep_hist, rep_bins = np.histogram(R, bins=20, range=(self.R_min, self.R_max))
+            data_file.create_dataset(f"rep_hist_{i}", data=rep_hist)
+            data_file.create_dataset(f"rep_bins_{i}", data=rep_bins)
+            data_file.create_dataset(f"Sn_snapshot_{i}", data=S.astype(np.int64))
+        if deferred is None:
+            write()
+        else:
+            deferred.append(write)
 
     def _write_final(self, data_file, ser, S, R):
         """Dataset names, order and dtypes of spgg.py:595-633."""
@@ -173,6 +181,39 @@ class SPGG:
         clusters, n_clusters = label(S == 0)
         sizes = np.bincount(clusters.ravel(), minlength=n_clusters + 1)[1:]
         data_file.create_dataset("cluster_sizes", data=sizes.astype(np.int64))
+
+
+class _HostWorker:
+    """Runs queued host jobs (snapshot post-processing) on one background thread, one batch at a
+    time; ctypes and NumPy release the GIL, so the jobs overlap the C call that enqueues and the
+    GPU that computes the next chunk.  Exceptions resurface in ``join``."""
+
+    def __init__(self):
+        self._thread = None
+        self._error = None
+
+    def run(self, jobs):
+        self.join()
+        if not jobs:
+            return
+        import threading
+
+        def body():
+            try:
+                for job in jobs:
+                    job()
+            except BaseException as e:   # re-raised on the caller's thread
+                self._error = e
+        self._thread = threading.Thread(target=body, daemon=True)
+        self._thread.start()
+
+    def join(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
 
 
 def run_models(models, filenames):
@@ -209,6 +250,7 @@ def run_models(models, filenames):
                  precision=precision, device=int(m0.params.get("device", 0)))
     files = [h5lite.open_file(f, "w") for f in filenames]
     results = []
+    worker = _HostWorker()
     try:
         for r, m in enumerate(models):
             q_host = m.q_table
@@ -223,10 +265,11 @@ def run_models(models, filenames):
         snaps = [{} for _ in models]
         t = 0                                       # iterations launched so far (running replicas are in lockstep)
         while t < T and not all(stopped):
+            host_work = []          # snapshot post-processing, run while the GPU computes the chunk
             if t in cut_points or (t == 0 and 1 in m0.snapshot_iters):
                 for r, m in enumerate(models):
                     if not stopped[r]:
-                        m._snapshot(eng, t + 1, files[r], snaps[r], r)
+                        m._snapshot(eng, t + 1, files[r], snaps[r], r, deferred=host_work)
             nxt = min([c for c in cut_points if c > t] + [T])
             k_req = min(nxt - t, chunk_max)
             if draws == "numpy":
@@ -242,7 +285,8 @@ def run_models(models, filenames):
                         if not (tag == "double_qlearning" and q == 1):  # Double-Q: rand, randint, rand
                             b[i, q] = m0._rng.randint(0, 2, size=(L, L))
                 eng.set_replay(u if pairs > 1 else u[:, 0], b if pairs > 1 else b[:, 0])
-            eng.step(k_req)
+            worker.run(host_work)   # histogram + HDF5 writes of the snapshots on a host thread ...
+            eng.step(k_req)         # ... while this call enqueues the chunk and the GPU computes it
             for r, m in enumerate(models):
                 if stopped[r]:
                     continue
@@ -256,8 +300,10 @@ def run_models(models, filenames):
                 if st.stopped_at >= 0 and st.stopped_at <= done[r]:
                     stopped[r] = True
                     if (done[r] + 1) in m.snapshot_iters and (done[r] + 1) not in snaps[r]:
+                        worker.join()
                         m._snapshot(eng, done[r] + 1, files[r], snaps[r], r)   # spgg.py:397 precedes :405
             t += k_req
+        worker.join()
         launches = int(eng.status().kernel_launches)
         for r, m in enumerate(models):
             S, R, Q = eng.get_state(r)
@@ -275,8 +321,9 @@ def run_models(models, filenames):
             # post-run attributes the reference leaves behind
             m.q_table, m.R, m._Sn = Q, R, S.astype(np.int64)
             m._S = [(m._Sn == j).astype(int) for j in range(m.num_of_strategies)]
-            for _ in range(done[r]):
-                m.algorithm.decay_epsilon()
+            if done[r]:                                  # decay_epsilon() done[r] times (algorithms.py:40-42)
+                m.algorithm.epsilon = float(series.epsilon_after(
+                    m.algorithm.epsilon, m.algorithm.epsilon_decay, m.algorithm.epsilon_min, done[r])[-1])
             m.epsilon = m.algorithm.epsilon
             m.avg_q_history = {k: list(ser[f"avg_{k}_history"]) for k in series.Q_NAMES}
             m.q_history_by_strategy = {
@@ -288,6 +335,10 @@ def run_models(models, filenames):
             nC = int((S == 0).sum())
             results.append((nC / N, (N - nC) / N, mean_P))
     finally:
+        try:
+            worker.join()          # never close a file under the writer thread
+        except BaseException:
+            pass
         for f in files:
             f.close()
         eng.close()
