@@ -82,6 +82,11 @@ struct spgg_handle {
   ResGeom rgeo{};
   size_t smem_res = 0;
   bool pend_resident = false;
+  bool res_grid = false;            // grid mode: one lattice over a cooperative grid (spgg_resident.cuh, GRID)
+  unsigned char *d_gimg = nullptr;
+  double *d_gpart = nullptr;
+  unsigned *d_gnsel = nullptr;
+  int gnsel_cap = 0;
   std::vector<double> eps_host;
   std::vector<uint32_t> thr_host;
   int replay_pairs = 1;
@@ -233,9 +238,18 @@ static res_fn_t pick_res2(int M, int action) {
 static res_fn_t pick_res(int M, int action, int L) {
   return (L % 4 == 0) ? pick_res2<true>(M, action) : pick_res2<false>(M, action);
 }
+template <bool FULL>
+static res_fn_t pick_resg2(int M, int action) {
+  if (M == 2) return action ? k_resident<2, true, FULL, true> : k_resident<2, false, FULL, true>;
+  return action ? k_resident<1, true, FULL, true> : k_resident<1, false, FULL, true>;
+}
+static res_fn_t pick_res_grid(int M, int action, int L) {
+  return (L % 4 == 0) ? pick_resg2<true>(M, action) : pick_resg2<false>(M, action);
+}
 // geometry of the decomposition into `cs` row blocks, or CS = 0 when a block does not fit on chip
-static ResGeom resident_geom(int L, int cs, size_t smem_limit) {
+static ResGeom resident_geom(int L, int cs, size_t smem_limit, int grid = 0) {
   ResGeom rg{};
+  rg.grid = grid;
   if (L < 2 * cs) cs = 1;  // a block needs two rows: its ghost rows come from the adjacent blocks only
   rg.rows_max = (L + cs - 1) / cs;
   rg.prow = rg.rows_max + 4;
@@ -303,6 +317,7 @@ static int free_all(spgg_handle *h) {
   cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_partials); cudaFree(h->d_tickets);
   cudaFree(h->d_stop); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_u); cudaFree(h->d_b);
   cudaFree(h->d_sc_S); cudaFree(h->d_sc_R); cudaFree(h->d_sc_Q); cudaFree(h->d_sc_info);
+  cudaFree(h->d_gimg); cudaFree(h->d_gpart); cudaFree(h->d_gnsel);
   return 0;
 }
 
@@ -414,6 +429,29 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
       h->smem_res = ResSmem(rg).total;
       // the opt-in is per function, not per handle: always the largest size any geometry may ask for
       CUDA_TRY(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    } else if (eligible && n_replicas == 1 && getenv("SPGG_NO_RESIDENT_GRID") == nullptr) {
+      // grid mode: a lone lattice too large for one cluster is spread over every SM (cooperative
+      // launch, one CTA per SM) as long as a row block still fits in shared memory
+      res_fn_t gf = pick_res_grid(h->M, h->action, h->g.L);
+      cudaFuncAttributes gfa;
+      CUDA_TRY(cudaFuncGetAttributes(&gfa, gf));
+      const size_t glim = prop0.sharedMemPerBlockOptin - gfa.sharedSizeBytes - 1024;
+      int coop = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+      const int nb_ctas = std::min(prop0.multiProcessorCount, g.L / 2);
+      ResGeom gg = resident_geom(g.L, nb_ctas, glim, 1);
+      if (coop && nb_ctas >= RES_RING && gg.CS == nb_ctas &&
+          cudaFuncSetAttribute(gf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)glim) == cudaSuccess) {
+        int occ_g = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, gf, gg.threads, ResSmem(gg).total) == cudaSuccess &&
+            (long long)occ_g * prop0.multiProcessorCount >= nb_ctas) {
+          h->resident = true;
+          h->res_grid = true;
+          h->rgeo = gg;
+          h->smem_res = ResSmem(gg).total;
+        }
+      }
+      (void)cudaGetLastError();
     }
   }
   g.TR = h->fast ? FTR : (g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4));
@@ -479,6 +517,10 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   ALLOC(h->d_partials, sizeof(double) * (size_t)n_replicas * g.ctas_per_rep * NSTAT);
   ALLOC(h->d_tickets, sizeof(unsigned) * n_replicas);
   ALLOC(h->d_stop, sizeof(int) * n_replicas);
+  if (h->res_grid) {
+    ALLOC(h->d_gimg, (size_t)h->rgeo.CS * 6 * h->rgeo.prow * h->rgeo.pitch);
+    ALLOC(h->d_gpart, sizeof(double) * (size_t)RES_RING * h->rgeo.CS * RES_NRED);
+  }
 #undef ALLOC
   if (h->fast) {
     const int rowsCR = FTR + 2 * h->M, rowsS = FTR + 4;
@@ -867,19 +909,37 @@ static int resident_chunk(spgg_handle *h, int n_steps, cudaStream_t st) {
     a.trace = d_tr;
   }
 #endif
+  a.gimg = h->d_gimg;
+  a.gpart = h->d_gpart;
+  a.gnsel = nullptr;
+  a.gmaxtab = reinterpret_cast<float *>(h->d_gmax);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(h->rgeo.CS * h->n_rep));
   cfg.blockDim = dim3((unsigned)h->rgeo.threads);
   cfg.dynamicSmemBytes = h->smem_res;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)h->rgeo.CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res(h->M, h->action, h->g.L), a));
+  if (h->res_grid) {
+    if (h->gnsel_cap < h->cap) {
+      cudaFree(h->d_gnsel);
+      h->d_gnsel = nullptr; h->gnsel_cap = 0;
+      CUDA_TRY(cudaMalloc((void **)&h->d_gnsel, sizeof(unsigned) * (size_t)h->cap));
+      h->gnsel_cap = h->cap;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_gnsel, 0, sizeof(unsigned) * (size_t)h->cap, st));
+    a.gnsel = h->d_gnsel;
+    attr[0].id = cudaLaunchAttributeCooperative;   // every block resident at once: grid-wide barriers
+    attr[0].val.cooperative = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res_grid(h->M, h->action, h->g.L), a));
+  } else {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)h->rgeo.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_res(h->M, h->action, h->g.L), a));
+  }
   {  // raw statistics rows -> public layout
     const int n_rows = n_steps + 1, total = n_rows * h->n_rep;
     k_resident_rows<<<(total + 127) / 128, 128, 0, st>>>(h->d_rc, h->d_stats, h->n_rep, h->cap, n_rows);

@@ -59,6 +59,7 @@ struct ResGeom {
   int pitch;     // bytes per plane row: RG + roundup(L,4) + RG, rounded up to 16
   int QR;        // quads (4 consecutive sites) per row: ceil(L / 4)
   int threads;
+  int grid;      // 1: grid mode (no reward plane, no cluster mailboxes in shared memory)
 };
 
 // byte offsets of the per-CTA shared-memory planes (identical in every CTA of a cluster, so a
@@ -70,7 +71,7 @@ struct ResSmem {
     const size_t nb = (size_t)rg.prow * rg.pitch;
     size_t o = 0;
     q = o; o += 4 * nq;
-    val = o; o += 4 * nb;
+    val = o; o += rg.grid ? 0 : 4 * nb;   // grid mode looks rewards up from the codes instead (room for 1000 x 1000)
     for (int i = 0; i < 2; ++i) { code[i] = o; o += nb; }
     for (int i = 0; i < 2; ++i) { R[i] = o; o += nb; }
     for (int i = 0; i < 2; ++i) { C[i] = o; o += nb; }
@@ -78,11 +79,11 @@ struct ResSmem {
     tab = o; o += 256 * sizeof(float);
     redf = o; o += sizeof(float) * (RES_THREADS / 32) * 32;
     redi = o; o += sizeof(unsigned) * (RES_NI + 2);
-    gmx = o; o += sizeof(float) * RES_CS_MAX;
-    nsel = o; o += sizeof(unsigned) * RES_CS_MAX;
+    gmx = o; o += rg.grid ? 0 : sizeof(float) * RES_CS_MAX;
+    nsel = o; o += rg.grid ? 0 : sizeof(unsigned) * RES_CS_MAX;
     o = (o + 15) / 16 * 16;
-    part = o; o += 2 * sizeof(double) * RES_CS_MAX * RES_NRED;  // two buffers, by iteration parity
-    ring = o; o += sizeof(double) * RES_RING * RES_RAW;         // finished raw rows waiting for their flush (rank 0)
+    part = o; o += rg.grid ? 0 : 2 * sizeof(double) * RES_CS_MAX * RES_NRED;  // two buffers, by iteration parity
+    ring = o; o += rg.grid ? 0 : sizeof(double) * RES_RING * RES_RAW;         // finished raw rows waiting for their flush (rank 0)
     total = (o + 15) / 16 * 16;
   }
 };
@@ -100,6 +101,12 @@ struct RArgs {
   int t0;             // iterations completed before this launch
   int n_steps;
   int cap;
+  // grid mode (one lattice over every SM, cooperative launch): global images of the byte planes the
+  // neighbours write ghost rows into, per-block statistics rows, per-iteration counters / maxima
+  unsigned char *gimg;   // [CS][6 * prow * pitch]
+  double *gpart;         // [RES_RING][CS][RES_NRED]
+  unsigned *gnsel;       // [cap]   cooperating actions chosen in iteration t0 + idx
+  float *gmaxtab;        // [n_rep][cap] lattice-global maxima (zeroed per chunk)
 #ifdef SPGG_RES_TRACE
   long long *trace;   // [n_rep * CS][8] accumulated cycles per phase
 #endif
@@ -139,6 +146,37 @@ __device__ __forceinline__ void load_win(ValWin<M> &w, const float *V, int base,
     }
   }
 }
+// the same window looked up from the reward codes (grid mode keeps no reward plane): byte b of the
+// code plane -> tab[b >> 1]
+template <int M, bool BELOW>
+__device__ __forceinline__ void load_win_code(ValWin<M> &w, const uint8_t *code, const float *tab, int base,
+                                              int pitch) {
+  auto row4 = [&](int at, float *dst) {
+    const uint32_t c = *reinterpret_cast<const uint32_t *>(code + at);
+    dst[0] = tab[(c >> 1) & 127u]; dst[1] = tab[(c >> 9) & 127u];
+    dst[2] = tab[(c >> 17) & 127u]; dst[3] = tab[c >> 25];
+  };
+  auto one = [&](int at) { return tab[code[at] >> 1]; };
+  row4(base, &w.c[2]);
+  w.c[1] = one(base - 1);
+  row4(base - pitch, &w.u[1]);
+  if constexpr (M == 2) {
+    w.c[0] = one(base - 2);
+    w.u[0] = one(base - pitch - 1);
+    w.u[5] = one(base - pitch + 4);
+    row4(base - 2 * pitch, &w.u2[0]);
+  }
+  if constexpr (BELOW) {
+    w.c[6] = one(base + 4);
+    row4(base + pitch, &w.d[1]);
+    if constexpr (M == 2) {
+      w.c[7] = one(base + 5);
+      w.d[0] = one(base + pitch - 1);
+      w.d[5] = one(base + pitch + 4);
+      row4(base + 2 * pitch, &w.d2[0]);
+    }
+  }
+}
 // reward of neighbour z (order of c_off: the value at (row - dx, col - dy)) of site k of the quad
 template <int M>
 __device__ __forceinline__ float win_nbr(const ValWin<M> &w, int k, int z) {
@@ -161,7 +199,11 @@ __device__ __forceinline__ float win_nbr(const ValWin<M> &w, int k, int z) {
 // FULL: L is a multiple of 4, so every quad is complete (no per-site validity branches: the four
 // sites of a quad are independent instruction streams the scheduler can interleave) and the
 // periodic column images are whole words.
-template <int M, bool ACTION, bool FULL>
+// GRID: instead of one cluster per replica, ONE lattice is spread over a cooperative grid of up to
+// one CTA per SM (lattices up to about 1100 x 1100): ghost rows travel through L2 (each block owns
+// a global image of its byte planes; neighbours write its ghost rows there and it pulls them after
+// the barrier), the maximum and the early-exit counter are global atomics, the barriers grid-wide.
+template <int M, bool ACTION, bool FULL, bool GRID = false>
 __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   constexpr int NK = (M == 2) ? 12 : 4;
   cg::cluster_group cluster = cg::this_cluster();
@@ -169,7 +211,8 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   const ResGeom &rg = a.rg;
   const int CS = rg.CS;
   const int rep = blockIdx.x / CS;
-  const int rank = (int)cluster.block_rank();
+  const int rank = GRID ? (int)(blockIdx.x % CS) : (int)cluster.block_rank();
+  cg::grid_group grid = cg::this_grid();
   const int L = g.L, pitch = rg.pitch, QR = rg.QR;
   const int W = pitch >> 2;  // 32-bit words per plane row
   const int base_rows = L / CS, rem = L % CS;
@@ -240,10 +283,19 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       sQf[(q_plane * 12) + o] = v.w;
     }
   }
-  unsigned char *smem_up = cluster.map_shared_rank(smem, up);
-  unsigned char *smem_dn = cluster.map_shared_rank(smem, down);
+  // where the ghost rows this block produces for its neighbours go: the neighbour's shared memory
+  // (DSMEM), or - grid mode - the neighbour's global plane image (same offsets as in shared memory)
+  const size_t img_stride = (size_t)6 * nb;
+  unsigned char *smem_up, *smem_dn;
+  if constexpr (GRID) {
+    smem_up = a.gimg + (size_t)up * img_stride - o_code0;
+    smem_dn = a.gimg + (size_t)down * img_stride - o_code0;
+  } else {
+    smem_up = cluster.map_shared_rank(smem, up);
+    smem_dn = cluster.map_shared_rank(smem, down);
+  }
   __syncthreads();
-  cluster.sync();  // every CTA of the cluster runs and has zeroed its planes before anyone pushes ghosts
+  if constexpr (!GRID) cluster.sync();  // every CTA of the cluster runs and has zeroed its planes before anyone pushes ghosts
 
   // ---- loop-invariant iteration patterns: plane words (row, word) and quads (row, quad)
   const int w_r0 = tid / W, w_c0 = tid % W, w_dr = nthr / W, w_dc = nthr % W;
@@ -278,7 +330,22 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
     __syncwarp();
     if (fs - ring_first == RES_RING - 1) flush_ring();
   };
-  int pend_s = -1;
+  // grid mode: the per-block rows of up to RES_RING iterations wait in HBM; block r folds the r-th
+  // pending iteration (fixed order over the blocks: deterministic) straight into its raw row
+  auto grid_fold = [&](int first, int last) {
+    const int fs = first + rank;
+    if (warp != 0 || fs > last) return;
+    double f = 0.0;
+    if (lane < RES_NRED) {
+      const double *pp = a.gpart + ((size_t)(fs % RES_RING) * CS) * RES_NRED + lane;
+      for (int k = 0; k < CS; ++k) f += __ldcg(pp + (size_t)k * RES_NRED);
+    }
+    double *row = a.stats + ((long long)rep * a.cap + fs) * NSTAT;
+    if (lane < RES_NRED) row[lane] = f;
+    if (lane == RES_NRED) row[RES_RAW_GMAX] = (double)__ldcg(a.gmaxtab + (long long)rep * a.cap + fs);
+  };
+  int gfold_first = 0;  // grid mode: first iteration whose block rows have not been folded yet
+  int pend_s = -1, last_s = -1;
   float pend_gm = 0.0f;
 
   int stop = a.stop_at[rep];
@@ -312,7 +379,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
         rr += w_dr; wq += w_dc;
         if (wq >= W) { wq -= W; rr += 1; }
       }
-      if (upd) {
+      if (upd && !GRID) {
         const uint32_t *cw = reinterpret_cast<const uint32_t *>(codeC);
         float4 *vw = reinterpret_cast<float4 *>(s_val);
         rr = w_r0; wq = w_c0;
@@ -338,7 +405,8 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       while (rr < nrow) {
         const int base = (rr + 2) * pitch + RG + 4 * qc;
         ValWin<M> w;
-        load_win<M, false>(w, s_val, base, pitch);
+        if constexpr (GRID) load_win_code<M, false>(w, codeC, s_tab, base, pitch);
+        else load_win<M, false>(w, s_val, base, pitch);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (FULL || 4 * qc + k < L) {
@@ -358,16 +426,24 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       if (lane == 0) atomicMax(&s_redi[RES_NI], wm);
       __syncthreads();
       RES_STAMP(1);  // phase 2 + block max
-      if (tid < CS) {
-        float *dst = reinterpret_cast<float *>(cluster.map_shared_rank(smem, tid) + lay.gmx);
-        dst[rank] = __uint_as_float(s_redi[RES_NI]);
+      if constexpr (GRID) {
+        if (tid == 0)  // non-negative IEEE floats order like unsigned integers; the table is zeroed per chunk
+          atomicMax(reinterpret_cast<unsigned *>(a.gmaxtab) + (long long)rep * a.cap + s, s_redi[RES_NI]);
+        grid.sync();
+        RES_STAMP(2);
+        gm = __ldcg(a.gmaxtab + (long long)rep * a.cap + s);
+      } else {
+        if (tid < CS) {
+          float *dst = reinterpret_cast<float *>(cluster.map_shared_rank(smem, tid) + lay.gmx);
+          dst[rank] = __uint_as_float(s_redi[RES_NI]);
+        }
+        cluster.barrier_arrive();
+        if (rank == 0 && warp == 0 && pend_s >= 0) do_fold(pend_s, pend_gm);
+        pend_s = -1;
+        cluster.barrier_wait();
+        RES_STAMP(2);  // max exchange + cluster barrier A (+ the previous iteration's statistics row on rank 0)
+        for (int k = 0; k < CS; ++k) gm = fmaxf(gm, s_gmx[k]);
       }
-      cluster.barrier_arrive();
-      if (rank == 0 && warp == 0 && pend_s >= 0) do_fold(pend_s, pend_gm);
-      pend_s = -1;
-      cluster.barrier_wait();
-      RES_STAMP(2);  // max exchange + cluster barrier A (+ the previous iteration's statistics row on rank 0)
-      for (int k = 0; k < CS; ++k) gm = fmaxf(gm, s_gmx[k]);
       inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));  // spgg.py:489 denominator
     }
 
@@ -443,7 +519,10 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
           }
         }
         ValWin<M> vw;
-        if constexpr (upd) load_win<M, true>(vw, s_val, base, pitch);
+        if constexpr (upd) {
+          if constexpr (GRID) load_win_code<M, true>(vw, codeC, s_tab, base, pitch);
+          else load_win<M, true>(vw, s_val, base, pitch);
+        }
         uint32_t sw = 0, coopw = 0, rneww = 0;  // new state / action / reputation bytes of the quad
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -607,29 +686,64 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
     if (tid < RES_NRED) {
       double x = 0.0;
       for (int w = 0; w < nwarp; ++w) x += (double)s_redf[w * 32 + tid];
-      double *dst = reinterpret_cast<double *>(cluster.map_shared_rank(smem, 0) + lay.part);
-      dst[(s & 1) * (RES_CS_MAX * RES_NRED) + rank * RES_NRED + tid] = x;
-      if (tid == 16)  // cooperating actions just chosen by this block: to every block (early-exit test)
-        for (int k = 0; k < CS; ++k)
-          reinterpret_cast<unsigned *>(cluster.map_shared_rank(smem, k) + lay.nsel)[rank] = (unsigned)x;
+      if constexpr (GRID) {
+        a.gpart[((size_t)(s % RES_RING) * CS + rank) * RES_NRED + tid] = x;
+        if (tid == 16 && x != 0.0) atomicAdd(a.gnsel + s, (unsigned)x);
+      } else {
+        double *dst = reinterpret_cast<double *>(cluster.map_shared_rank(smem, 0) + lay.part);
+        dst[(s & 1) * (RES_CS_MAX * RES_NRED) + rank * RES_NRED + tid] = x;
+        if (tid == 16)  // cooperating actions just chosen by this block: to every block (early-exit test)
+          for (int k = 0; k < CS; ++k)
+            reinterpret_cast<unsigned *>(cluster.map_shared_rank(smem, k) + lay.nsel)[rank] = (unsigned)x;
+      }
     }
     RES_STAMP(4);  // reductions + block barrier + pushes
-    cluster.sync();  // ghost rows, partial rows and counters of every block have landed
-    RES_STAMP(5);  // cluster barrier B
+    if constexpr (GRID) {
+      grid.sync();  // ghost rows (in the global images), block rows and counters have landed in L2
+      RES_STAMP(5);
+      if (sel) {
+        // pull this block's ghost rows of the planes just written out of its global image (L2 loads:
+        // the neighbours' stores never passed through this SM's L1)
+        const uint32_t *img = reinterpret_cast<const uint32_t *>(a.gimg + (size_t)rank * img_stride);
+        uint32_t *pl = reinterpret_cast<uint32_t *>(smem + o_code0);
+        const int nbw = nb >> 2;
+        for (int e = tid; e < 12 * W; e += nthr) {
+          const int z = e / (4 * W), rem4 = e - z * (4 * W), gr = rem4 / W, wq = rem4 - gr * W;
+          const int prow_ = (gr < 2) ? gr : nrow + gr;   // plane rows 0,1 and nrow+2, nrow+3
+          const int at = (2 * z + (cur ^ 1)) * nbw + prow_ * W + wq;
+          pl[at] = __ldcg(img + at);
+        }
+        __syncthreads();  // the ghost rows are in place before the next iteration reads them
+      }
+      if ((s % RES_RING) == RES_RING - 1) {
+        grid_fold(gfold_first, s);
+        gfold_first = s + 1;
+      }
+    } else {
+      cluster.sync();  // ghost rows, partial rows and counters of every block have landed
+      RES_STAMP(5);  // cluster barrier B
+    }
 
     if (sel) {
       // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405)
       long long tot = 0;
-      for (int k = 0; k < CS; ++k) tot += s_nsel[k];
+      if constexpr (GRID) {
+        tot = __ldcg(a.gnsel + s);
+      } else {
+        for (int k = 0; k < CS; ++k) tot += s_nsel[k];
+      }
       if (tot == 0 || tot == n_sites) stop = j + 1;
       cur ^= 1;
     }
-    pend_s = s; pend_gm = gm;  // the row is folded inside the next barrier window
+    last_s = s;
+    if constexpr (!GRID) { pend_s = s; pend_gm = gm; }  // the row is folded inside the next barrier window
     if (tid <= RES_NI) s_redi[tid] = 0u;  // next use is behind the next block barrier
     RES_STAMP(6);  // early-exit test, fold and statistics row (rank 0)
   }
 
-  if (rank == 0 && warp == 0) {
+  if constexpr (GRID) {
+    if (last_s >= gfold_first) grid_fold(gfold_first, last_s);   // visible since the last grid barrier
+  } else if (rank == 0 && warp == 0) {
     if (pend_s >= 0) do_fold(pend_s, pend_gm);
     flush_ring();
   }

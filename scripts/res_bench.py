@@ -24,7 +24,10 @@ only = sys.argv[1:]
 out = {}
 cases = [("c1_L100", dict(C1, L=100), 1), ("c2_L200_act_m2", dict(C2, L=200), 1), ("c1_L200", dict(C1, L=200), 1),
          ("c1_L100x10", dict(C1, L=100), 10), ("c1_L200x18", dict(C1, L=200), 18), ("c1_L200x60", dict(C1, L=200), 60),
-         ("c1_L240", dict(C1, L=240), 1), ("c1_L64", dict(C1, L=64), 1)]
+         ("c1_L240", dict(C1, L=240), 1), ("c1_L64", dict(C1, L=64), 1),
+         # grid mode (cooperative launch over every SM)
+         ("c1_L400", dict(C1, L=400), 1), ("c1_L512", dict(C1, L=512), 1), ("c1_L1000", dict(C1, L=1000), 1),
+         ("c2_L1000_act_m2", dict(C2, L=1000), 1), ("c1_L1024", dict(C1, L=1024), 1)]
 for name, p, nrep in cases:
     if only and name not in only: continue
     p = full_params(p)
