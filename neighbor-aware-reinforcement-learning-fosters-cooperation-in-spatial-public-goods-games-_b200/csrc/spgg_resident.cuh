@@ -334,15 +334,28 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   // pending iteration (fixed order over the blocks: deterministic) straight into its raw row
   auto grid_fold = [&](int first, int last) {
     const int fs = first + rank;
-    if (warp != 0 || fs > last) return;
-    double f = 0.0;
-    if (lane < RES_NRED) {
+    if (fs > last) return;  // block-uniform
+    // up to 16 warps read interleaved slices of the block rows (independent L2 loads in flight),
+    // warp 0 adds the slice sums in order; the N plane is free between two iterations: scratch
+    double *scr = reinterpret_cast<double *>(s_N);
+    const int P = min(nwarp, 16);
+    if (warp < P && lane < RES_NRED) {
       const double *pp = a.gpart + ((size_t)(fs % RES_RING) * CS) * RES_NRED + lane;
-      for (int k = 0; k < CS; ++k) f += __ldcg(pp + (size_t)k * RES_NRED);
+      double f = 0.0;
+#pragma unroll 4
+      for (int k = warp; k < CS; k += P) f += __ldcg(pp + (size_t)k * RES_NRED);
+      scr[warp * 32 + lane] = f;
     }
-    double *row = a.stats + ((long long)rep * a.cap + fs) * NSTAT;
-    if (lane < RES_NRED) row[lane] = f;
-    if (lane == RES_NRED) row[RES_RAW_GMAX] = (double)__ldcg(a.gmaxtab + (long long)rep * a.cap + fs);
+    __syncthreads();
+    if (warp == 0) {
+      double f = 0.0;
+      if (lane < RES_NRED)
+        for (int j = 0; j < P; ++j) f += scr[j * 32 + lane];
+      double *row = a.stats + ((long long)rep * a.cap + fs) * NSTAT;
+      if (lane < RES_NRED) row[lane] = f;
+      if (lane == RES_NRED) row[RES_RAW_GMAX] = (double)__ldcg(a.gmaxtab + (long long)rep * a.cap + fs);
+    }
+    __syncthreads();  // the scratch is the N plane again
   };
   int gfold_first = 0;  // grid mode: first iteration whose block rows have not been folded yet
   int pend_s = -1, last_s = -1;
@@ -451,6 +464,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
     // action of iteration j+1, update the reputation, emit the reward code of j+1
     // packed per-thread counters (a thread visits at most 128 sites per iteration): 8-bit class
     // counts (class = C_old*2 + coop), 16-bit SigmaN sums per class, 10-bit group histogram
+    unsigned gnsel_v = 0;
     unsigned pk_n = 0;
     unsigned long long pk_sn = 0, pk_grp = 0;
     unsigned n_best = 0, n_best2 = 0, n_sel_coop = 0;
@@ -701,17 +715,28 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
     if constexpr (GRID) {
       grid.sync();  // ghost rows (in the global images), block rows and counters have landed in L2
       RES_STAMP(5);
+      if (sel) gnsel_v = __ldcg(a.gnsel + s);  // in flight while the ghost rows are pulled
       if (sel) {
         // pull this block's ghost rows of the planes just written out of its global image (L2 loads:
         // the neighbours' stores never passed through this SM's L1)
         const uint32_t *img = reinterpret_cast<const uint32_t *>(a.gimg + (size_t)rank * img_stride);
         uint32_t *pl = reinterpret_cast<uint32_t *>(smem + o_code0);
         const int nbw = nb >> 2;
-        for (int e = tid; e < 12 * W; e += nthr) {
-          const int z = e / (4 * W), rem4 = e - z * (4 * W), gr = rem4 / W, wq = rem4 - gr * W;
+        // a warp per (plane, ghost row): no index divisions, eight independent L2 loads in flight per
+        // lane, so the pull costs about one L2 round trip
+        for (int r12 = warp; r12 < 12; r12 += nwarp) {
+          const int z = r12 >> 2, gr = r12 & 3;
           const int prow_ = (gr < 2) ? gr : nrow + gr;   // plane rows 0,1 and nrow+2, nrow+3
-          const int at = (2 * z + (cur ^ 1)) * nbw + prow_ * W + wq;
-          pl[at] = __ldcg(img + at);
+          const int row_at = (2 * z + (cur ^ 1)) * nbw + prow_ * W;
+          for (int w0 = lane; w0 < W; w0 += 32 * 8) {
+            uint32_t tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (w0 + 32 * u < W) tmp[u] = __ldcg(img + row_at + w0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (w0 + 32 * u < W) pl[row_at + w0 + 32 * u] = tmp[u];
+          }
         }
         __syncthreads();  // the ghost rows are in place before the next iteration reads them
       }
@@ -728,7 +753,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
       // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405)
       long long tot = 0;
       if constexpr (GRID) {
-        tot = __ldcg(a.gnsel + s);
+        tot = gnsel_v;
       } else {
         for (int k = 0; k < CS; ++k) tot += s_nsel[k];
       }
