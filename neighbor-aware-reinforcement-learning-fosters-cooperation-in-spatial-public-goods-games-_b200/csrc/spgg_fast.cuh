@@ -141,10 +141,6 @@ __device__ __forceinline__ void tma_store_wait_read_n() {
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// programmatic dependent launch: let the next kernel of the stream be scheduled while this one
-// drains, and wait (in the next kernel) until everything before it has completed and is visible
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // bytes of the column-shifted neighbours of a 4-site word
@@ -654,7 +650,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   v[ST_N_BEST_2ND] = (double)(pk_best >> 16);
   v[ST_X_NSEL] = (double)n_sel;
   __syncthreads();
-  block_reduce<NSTAT>(v, sm_red);
+  block_reduce_bfly<NSTAT>(v, sm_red);
   double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
   if (tid < NSTAT) part[tid] = sm_red[tid];
   __threadfence();

@@ -110,6 +110,11 @@ struct KArgs {
 #endif
 };
 
+// programmatic dependent launch: let the next kernel of the stream be scheduled while this one
+// drains, and wait (in the next kernel) until everything before it has completed and is visible
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
@@ -283,7 +288,51 @@ __device__ __forceinline__ void load_coop_tile(uint8_t *sm, const uint32_t *bits
   }
 }
 
-// deterministic block reduction of NV doubles held per thread; result in sm_red[0..NV)
+// deterministic block reduction of NV doubles held per thread; result in sm_red[0..NV).
+// Warp stage: groups of 32 values go through one transposing butterfly (at each of five levels a
+// lane keeps half of its values and hands the other half to its partner: 31 shuffles reduce 32
+// values at once and lane z ends with the warp sum of value z); the remaining NV % 32 values take
+// the classic five-step tree.
+template <int NV>
+__device__ __forceinline__ void block_reduce_bfly(double (&v)[NV], double *sm_red /* [8][NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  constexpr int NG = NV / 32;
+#pragma unroll
+  for (int gI = 0; gI < NG; ++gI) {
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = v[32 * gI + i];
+#pragma unroll
+    for (int lvl = 0; lvl < 5; ++lvl) {
+      const int o = 16 >> lvl, half = 16 >> lvl;
+      const bool hi = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const double keep = hi ? w[i + half] : w[i];
+        const double send = hi ? w[i] : w[i + half];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    sm_red[warp * NV + 32 * gI + lane] = w[0];
+  }
+#pragma unroll
+  for (int i = 32 * NG; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm_red[warp * NV + i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = 0.0;
+    for (int w = 0; w < nw; ++w) x += sm_red[w * NV + threadIdx.x];
+    sm_red[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
+// the same with one five-step tree per value: fewer live registers (the general kernel keeps its
+// occupancy), five times the shuffles
 template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], double *sm_red /* [8][NV] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -394,6 +443,9 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
   constexpr int NK = (M == 2) ? 12 : 4;
   const Geom &g = a.g;
   const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  // launched with programmatic stream serialization only when a launch is short (spgg_capi.cu)
+  pdl_launch_dependents();
+  pdl_wait();  // the code plane and the stop flags come from the k_step before this kernel
   const int stop = a.stop_at[rep];
   if (stop >= 0 && a.j > stop) return;
 
@@ -504,6 +556,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
   constexpr bool kI8 = (sizeof(RT) == 1);
   const Geom &g = a.g;
   const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  pdl_launch_dependents();  // see k_gmax
+  pdl_wait();  // the planes, the stop flags and gmax come from the kernels before this one
   const int stop = a.stop_at[rep];
   if (stop >= 0 && a.j > stop) return;
   const bool upd = a.do_update != 0;
