@@ -619,7 +619,6 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     }
     ty = nty; txs = ntxs; tx = ntx;
   }
-  if (lane == 0 && (upd || (tid == 0 && sel))) tma_store_wait_all();  // Q segments / tile planes in flight
 
 #ifdef SPGG_TRACE
   if (tid == 0 && a.trace) {
@@ -654,6 +653,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
   if (tid < NSTAT) part[tid] = sm_red[tid];
   __threadfence();
+  // the last tile's Q segments / tile planes were left in flight while the statistics were reduced
+  if (lane == 0 && (upd || (tid == 0 && sel))) tma_store_wait_all();
   __syncthreads();
   if (tid == 0) {
     const unsigned t = atomicInc(a.tickets + rep, (unsigned)g.ctas_per_rep - 1u);

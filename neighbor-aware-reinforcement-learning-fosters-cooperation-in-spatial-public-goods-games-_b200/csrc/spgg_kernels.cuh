@@ -360,7 +360,8 @@ __device__ __forceinline__ void fold_partials(const double *pp, int n_ctas, doub
   const int q = threadIdx.x / NSTAT, z = threadIdx.x - q * NSTAT;
   if (q < groups) {
     double x = 0.0;
-#pragma unroll 4
+    // sixteen independent L2 loads in flight per thread: this fold is the tail of every launch
+#pragma unroll 16
     for (int c = q; c < n_ctas; c += groups) x += __ldcg(pp + (long long)c * NSTAT + z);
     sm_red[q * NSTAT + z] = x;
   }
