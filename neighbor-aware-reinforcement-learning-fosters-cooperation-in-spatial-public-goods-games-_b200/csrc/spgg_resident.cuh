@@ -13,7 +13,13 @@
 //     shared memory through DSMEM by the thread that produces them;
 //   * the lattice-global max |reward difference| (spgg.py:488) is an all-to-all of one float
 //     per CTA through DSMEM; the early-exit test (spgg.py:405) the same with one counter;
-//   * two cluster barriers per iteration replace two kernel launches.
+//   * two cluster barriers per iteration replace two kernel launches;
+//   * statistics: one transposing butterfly per warp for all 28 values, block rows folded by rank
+//     0 inside the next barrier window into an on-chip ring of raw rows (k_resident_rows turns
+//     them into the public layout once per chunk).
+//
+// GRID mode (template flag) spreads ONE lattice of up to 1036 x 1036 sites over a cooperative grid
+// of one CTA per SM with the same quad code: ghost rows, maxima and counters travel through L2.
 //
 // Arithmetic, Philox counters and statistics are those of k_step<ModeF32I8> / k_gmax
 // (Q-learning, algorithms.py:96-133), so S, R and Q are bit-identical to the other two paths.
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resident(RArgs a) {
   float *s_tab = reinterpret_cast<float *>(smem + lay.tab);
   float *s_ratio = s_tab + 128;
   float *s_redf = reinterpret_cast<float *>(smem + lay.redf);
-  unsigned *s_redi = reinterpret_cast<unsigned *>(smem + lay.redi);  // [RES_NI] sums, [RES_NI] = block max
+  unsigned *s_redi = reinterpret_cast<unsigned *>(smem + lay.redi);  // [RES_NI] = block max of the reward differences
   float *s_gmx = reinterpret_cast<float *>(smem + lay.gmx);
   unsigned *s_nsel = reinterpret_cast<unsigned *>(smem + lay.nsel);
   double *s_part = reinterpret_cast<double *>(smem + lay.part);
