@@ -98,3 +98,30 @@ def test_unsupported_inputs(tmp_path):
         assert f["f32"].dtype == np.float32
         with pytest.raises(OSError):
             f.create_dataset("z", data=np.zeros(1))
+
+
+def test_large_datasets_stream_to_disk_and_read_back(tmp_path):
+    """Datasets above the in-memory threshold are written when created (no staging copy of the
+    whole file) and stay readable through the open writer and after reopening."""
+    path = str(tmp_path / "big.h5")
+    rs = np.random.RandomState(0)
+    big = rs.rand(600, 600)                       # 2.9 MB > KEEP_BYTES
+    ints = rs.randint(0, 2, (700, 700))           # int64, 3.9 MB
+    with h5lite.File(path, "w") as f:
+        f.create_dataset("small_before", data=np.arange(5.0))
+        f.create_dataset("R_snapshot_1", data=big)
+        f.create_dataset("Sn_snapshot_1", data=ints)
+        f.create_dataset("small_after", data=np.arange(7, dtype=np.int64))
+        assert np.array_equal(f["R_snapshot_1"][:], big)          # read back from the open writer
+        assert f["Sn_snapshot_1"].shape == (700, 700)
+        big[0, 0] = -1.0                                          # the file already holds the data
+    with h5lite.File(path, "r") as f:
+        assert sorted(f.keys()) == ["R_snapshot_1", "Sn_snapshot_1", "small_after", "small_before"]
+        got = f["R_snapshot_1"][:]
+        assert got[0, 0] != -1.0 and np.array_equal(got[1:], big[1:])
+        assert np.array_equal(f["Sn_snapshot_1"][:], ints)
+        assert f["small_after"][:].tolist() == list(range(7))
+    # every data block is 8-byte aligned and inside the file
+    buf = open(path, "rb").read()
+    eof, = struct.unpack_from("<Q", buf, 40)
+    assert eof == len(buf)

@@ -129,3 +129,46 @@ def test_runner_folder_names_and_tuple_formats():
     with pytest.raises(ValueError):
         runner._unpack((1, 2, 3))
     assert runner.RUNNER_MODEL["L"] == 100 and runner.RUNNER_MODEL["iterations"] == 100001
+
+
+def test_epsilon_series_matches_the_iterated_rule():
+    """series.epsilon_after vectorises e <- max(e*decay, eps_min) (algorithms.py:40-42); it must
+    reproduce the iterated roundings exactly, including degenerate parameters."""
+    import numpy as np
+    from spgg_b200 import series
+
+    def ref(e, d, m, n):
+        out = []
+        for _ in range(n):
+            e = max(e * d, m)
+            out.append(e)
+        return np.array(out)
+
+    cases = [(0.5, 0.99, 0.01, 2000), (0.5, 0.995, 0.01, 30000), (0.5, 1.0, 0.01, 50), (0.0, 0.99, 0.0, 30),
+             (0.5, 0.99, 0.5, 10), (0.3, 0.9, 0.0, 500), (0.5, 1.5, 0.01, 20), (0.5, 0.0, 0.01, 5),
+             (0.005, 0.99, 0.01, 8), (0.5, 0.99, 0.01, 0)]
+    for e, d, m, n in cases:
+        assert np.array_equal(series.epsilon_after(e, d, m, n), ref(e, d, m, n)), (e, d, m, n)
+
+
+def test_host_worker_runs_jobs_in_order_and_reraises():
+    """The snapshot post-processing thread of SPGG.run: batches run in submission order, one at a
+    time, and an exception in a job resurfaces on the caller's thread."""
+    import pytest
+    from spgg_b200.spgg import _HostWorker
+    out = []
+    w = _HostWorker()
+    w.run([lambda: out.append(1), lambda: out.append(2)])
+    w.run([lambda: out.append(3)])          # joins the first batch before starting the second
+    w.join()
+    assert out == [1, 2, 3]
+    w.run([])                               # nothing to do: no thread
+    w.join()
+
+    def boom():
+        raise ValueError("disk full")
+    w.run([boom, lambda: out.append(4)])
+    with pytest.raises(ValueError, match="disk full"):
+        w.join()
+    assert out == [1, 2, 3]                 # jobs after the failing one are not run
+    w.join()                                # the error is reported once
