@@ -155,6 +155,11 @@ int spgg_sync(spgg_t *h);
 int spgg_get_stats(spgg_t *h, int replica, int first, int n, double *rows_out);
 int spgg_query(spgg_t *h, int replica, spgg_status_t *out);
 
+/* Which kernels serve this handle, as text ("resident: cluster of 16 CTAs x 352 threads ...",
+ * "resident: cooperative grid of 148 CTAs ...", "fast: TMA-staged tiles ...", "general: ...").
+ * Writes at most n bytes including the terminating NUL; returns the length it needed. */
+int spgg_describe(spgg_t *h, char *buf, int n);
+
 /* Strip decomposition (multi-GPU): boundary rows <-> ghost rows.  pack copies
  * the rows a neighbour needs into two contiguous device buffers of
  * spgg_halo_bytes() each (up = towards row0-1, down = towards row0+rows);

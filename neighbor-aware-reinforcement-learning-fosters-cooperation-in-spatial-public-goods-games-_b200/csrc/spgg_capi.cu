@@ -1000,6 +1000,30 @@ extern "C" int spgg_query(spgg_t *h, int rep, spgg_status_t *out) {
   return SPGG_OK;
 }
 
+extern "C" int spgg_describe(spgg_t *h, char *buf, int n) {
+  if (!h) return fail(SPGG_E_INVALID, "null handle");
+  char tmp[256];
+  const char *arith = h->mode == MODE_F64 ? "fp64 Q and R" : (h->mode == MODE_F32_F ? "fp32 Q, fp32 R" : "fp32 Q, int8 R");
+  int len;
+  if (h->resident && h->res_grid)
+    len = snprintf(tmp, sizeof(tmp), "resident: cooperative grid of %d CTAs x %d threads, %zu KB shared memory per CTA, "
+                   "ghost rows through L2 (%s)", h->rgeo.CS, h->rgeo.threads, h->smem_res >> 10, arith);
+  else if (h->resident)
+    len = snprintf(tmp, sizeof(tmp), "resident: cluster of %d CTAs x %d threads per replica, %zu KB shared memory per CTA, "
+                   "ghost rows through DSMEM (%s)", h->rgeo.CS, h->rgeo.threads, h->smem_res >> 10, arith);
+  else if (h->fast)
+    len = snprintf(tmp, sizeof(tmp), "fast: TMA-staged %dx%d tiles, %d persistent CTAs per replica, two launches per iteration (%s)",
+                   FTR, TC, h->g.ctas_per_rep, arith);
+  else
+    len = snprintf(tmp, sizeof(tmp), "general: %dx%d tiles, %d CTAs per replica, two launches per iteration (%s)", h->g.TR, TC,
+                   h->g.ctas_per_rep, arith);
+  if (buf && n > 0) {
+    strncpy(buf, tmp, (size_t)n - 1);
+    buf[n - 1] = 0;
+  }
+  return len + 1;
+}
+
 // device-side random initial state (distributions of spgg.py:121,129,162)
 extern "C" int spgg_init_random(spgg_t *h, int rep, uint64_t seed) {
   if (!h) return fail(SPGG_E_INVALID, "null handle");

@@ -148,6 +148,12 @@ class Engine:
         L_.check(self.lib.spgg_get_stats(self._h, replica, first, n, out.ctypes.data))
         return out
 
+    def describe(self) -> str:
+        """Which kernels serve this handle (resident cluster / cooperative grid, TMA fast path, general)."""
+        buf = C.create_string_buffer(256)
+        self.lib.spgg_describe(self._h, buf, 256)
+        return buf.value.decode()
+
     def status(self, replica: int = 0) -> L_.Status:
         st = L_.Status()
         L_.check(self.lib.spgg_query(self._h, replica, C.byref(st)))

@@ -84,6 +84,8 @@ def test_resident_equals_per_iteration_kernels(monkeypatch, name, p):
         else:
             monkeypatch.delenv("SPGG_NO_RESIDENT", raising=False)
         eng = _engine(p, seeds=777, precision="fp32")
+        want = ("cooperative grid" if name.startswith("grid_") else "resident: cluster") if not no_res else "two launches"
+        assert want in eng.describe(), eng.describe()
         eng.set_state(S0, np.zeros((L, L)), Q0)
         l0 = eng.status().kernel_launches
         eng.step(n)
