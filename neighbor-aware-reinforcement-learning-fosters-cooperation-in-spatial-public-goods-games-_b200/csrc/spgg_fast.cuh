@@ -160,7 +160,7 @@ struct FastMaps {
 // UPD / SEL are compile-time so the four sites a thread handles per row form one straight-line
 // block the scheduler can interleave.
 template <int M, bool ACTION, bool UPD, bool SEL>
-__device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &a, bool prologue_done) {
+__device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &a) {
   typedef FastSmem<M> SM;
   constexpr int NK = (M == 2) ? 12 : 4;
   constexpr bool upd = UPD, sel = SEL;
@@ -187,28 +187,17 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   unsigned long long t_start = 0;
   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 #endif
-  if (!prologue_done) {
-    // everything that does not depend on the previous kernels runs before griddepcontrol.wait: it
-    // overlaps the tail of the kernel in front (programmatic dependent launch)
-    for (int i = tid; i < (int)(sizeof(RepConst) / 4); i += FTHREADS)
-      reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
-    if (tid == 0) {
-      mbar_init(&bars[0], 1);
-      mbar_init(&bars[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    for (int i = tid; i < 128; i += FTHREADS) {
-      sm_tab[i] = s_rc.rewtab[i];
-      sm_ratio[i] = s_rc.ratiotab[i];
-    }
-    pdl_wait();  // the planes, the stop flags and gmax come from the kernels before this one
-    const int stop = a.stop_at[rep];
-    if (stop >= 0 && a.j > stop) return;
-    if (SEL && stop >= 0 && a.j == stop) {  // uniform lattice: finish iteration j, choose nothing (spgg.py:405)
-      if constexpr (UPD) step_fast_body<M, ACTION, true, false>(tm, a, true);
-      return;
-    }
+  for (int i = tid; i < (int)(sizeof(RepConst) / 4); i += FTHREADS)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  for (int i = tid; i < 128; i += FTHREADS) {
+    sm_tab[i] = s_rc.rewtab[i];
+    sm_ratio[i] = s_rc.ratiotab[i];
   }
   const RepConst &rc = s_rc;
 
@@ -710,7 +699,15 @@ template <int M, bool ACTION, bool UPD, bool SEL>
 __global__ void __launch_bounds__(FTHREADS, SPGG_FAST_MINBLOCKS)
 k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   pdl_launch_dependents();
-  step_fast_body<M, ACTION, UPD, SEL>(tm, a, false);
+  pdl_wait();  // the planes, the stop flags and gmax come from the kernels before this one
+  const int rep = blockIdx.x / a.g.ctas_per_rep;
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  if (SEL && stop >= 0 && a.j == stop) {  // uniform lattice: finish iteration j, choose nothing (spgg.py:405)
+    if constexpr (UPD) step_fast_body<M, ACTION, true, false>(tm, a);
+    return;
+  }
+  step_fast_body<M, ACTION, UPD, SEL>(tm, a);
 }
 
 // lattice-global max |reward difference| of iteration j (spgg.py:486-488), fast path.
