@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SPGG_ABI_VERSION 1
+#define SPGG_ABI_VERSION 2
 
 /* error codes */
 #define SPGG_OK 0
@@ -118,11 +118,34 @@ void spgg_destroy(spgg_t *h);
 
 /* Upload q_table (rows*L*2*2 doubles, layout of spgg.py:121), R (rows*L
  * doubles, spgg.py:129) and _Sn (rows*L bytes, 0=C 1=D, spgg.py:162) of one
- * replica.  Resets that replica's iteration counter and epsilon.
+ * replica.  Resets that replica's epsilon to its ctor value.
+ *
+ * The iteration counter (Philox counter word, row index of the statistics) is
+ * HANDLE-WIDE.  The first spgg_set_state / spgg_init_random after iterations
+ * have run starts a new run: the counter returns to 0 and every OTHER replica
+ * of a batch is marked stale; spgg_step / spgg_begin_steps fail with
+ * SPGG_E_STATE until each stale replica has been given a state too.  To continue
+ * a run instead of starting one, follow the uploads with spgg_set_progress.
  * SPGG_ALGO_DOUBLE_QLEARNING: Q holds both tables, rows*L*2*2*2 doubles laid out
  * [site][table][state][action] (q_table_1, q_table_2 of algorithms.py:245-260). */
 int spgg_set_state(spgg_t *h, int replica, const uint8_t *S, const double *R, const double *Q);
 int spgg_get_state(spgg_t *h, int replica, uint8_t *S, double *R, double *Q);
+
+/* Checkpoint / resume (the reference can only inject strategies, S_in_one
+ * spgg.py:51,133,161): declare that the states just uploaded are those after
+ * `iteration` completed iterations, with exploration rates epsilon[0..n_replicas)
+ * (spgg_query reports both).  The Philox counters, the epsilon schedule
+ * (algorithms.py:40-42) and the early-exit bookkeeping continue from there, so
+ * n iterations == k iterations + spgg_get_state + spgg_destroy + spgg_create +
+ * spgg_set_state + spgg_set_progress + (n-k) iterations, bit for bit. */
+int spgg_set_progress(spgg_t *h, int64_t iteration, const double *epsilon);
+
+/* Position-keyed 64-bit digests of one replica's owned rows: out[0] strategies,
+ * out[1] reputations, out[2] Q.  A site contributes hash(global row, column) *
+ * (bits of its value as a double + 1) mod 2^64, so the digests of the strips of a
+ * lattice add up (mod 2^64) to the digest of the whole lattice: multi-GPU runs are
+ * compared with single-GPU runs without moving a 20 GB state through the host. */
+int spgg_state_digest(spgg_t *h, int replica, uint64_t out[3]);
 
 /* Same distributions as the reference ctor (Q ~ U(-0.01,0.01) spgg.py:121, R = 0
  * spgg.py:129, S ~ Bernoulli(1/2) spgg.py:162) generated on the device from Philox

@@ -57,7 +57,8 @@ EXPORTS = (
     "spgg_step", "spgg_sync", "spgg_get_stats", "spgg_query", "spgg_halo_bytes",
     "spgg_halo_pack", "spgg_halo_unpack", "spgg_phase_kernel", "spgg_phase_gmax",
     "spgg_gmax_device_ptr", "spgg_begin_steps", "spgg_end_steps", "spgg_last_error",
-    "spgg_abi_version", "spgg_init_random", "spgg_describe",
+    "spgg_abi_version", "spgg_init_random", "spgg_describe", "spgg_set_progress",
+    "spgg_state_digest",
 )
 
 _lib = None
@@ -97,6 +98,8 @@ def load():
     lib.spgg_end_steps.argtypes = [vp, vp]
     lib.spgg_init_random.argtypes = [vp, i32, C.c_uint64]
     lib.spgg_describe.argtypes = [vp, C.c_char_p, i32]
+    lib.spgg_set_progress.argtypes = [vp, i64, vp]
+    lib.spgg_state_digest.argtypes = [vp, i32, vp]
     lib.spgg_last_error.restype = C.c_char_p
     lib.spgg_abi_version.restype = i32
     _lib = lib

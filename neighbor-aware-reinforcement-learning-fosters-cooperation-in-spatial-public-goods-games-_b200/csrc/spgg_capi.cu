@@ -95,6 +95,7 @@ struct spgg_handle {
   long long iter = 0;
   std::vector<double> eps_cur;     // eps used at iteration iter+1
   std::vector<long long> stop_at;  // -1 or the t with uniform S_t
+  std::vector<char> stale;         // replica still holds the state of the previous run (include/spgg.h)
   long long launches = 0;
   // pending asynchronous chunk
   bool pending = false;
@@ -543,6 +544,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   h->eps_cur.resize(n_replicas);
   for (int r = 0; r < n_replicas; ++r) h->eps_cur[r] = params[r].epsilon;
   h->stop_at.assign(n_replicas, -1);
+  h->stale.assign(n_replicas, 0);
   *out = h;
   return SPGG_OK;
 }
@@ -621,6 +623,16 @@ static int ensure_scratch(spgg_handle *h, bool want_q) {
   return SPGG_OK;
 }
 
+// a state upload after iterations have run starts a new run (include/spgg.h): the handle-wide
+// iteration counter rewinds and the other replicas must be given a state before stepping
+static void begin_new_run(spgg_handle *h, int rep) {
+  if (h->iter != 0) {
+    h->iter = 0;
+    std::fill(h->stale.begin(), h->stale.end(), 1);
+  }
+  h->stale[rep] = 0;
+}
+
 extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double *R, const double *Q) {
   if (!h || !S || !R || !Q) return fail(SPGG_E_INVALID, "spgg_set_state: null argument");
   if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
@@ -654,7 +666,7 @@ extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double
   if (info[0] == 1) return fail(SPGG_E_INVALID, "strategy array holds values other than 0/1");
   if (info[0] == 2)
     return fail(SPGG_E_INVALID, "R is not representable in int8 units of %g; use r_storage=FP32", rc.rq);
-  if (rep == 0) h->iter = 0;
+  begin_new_run(h, rep);
   h->eps_cur[rep] = h->params[rep].epsilon;
   int stop = -1;
   if (g.wrap_rows && (info[1] == 0 || info[1] == (unsigned long long)g.site_stride))
@@ -751,6 +763,10 @@ extern "C" int spgg_begin_steps(spgg_t *h, int n_steps, void *stream_) {
   if (n_steps < 1) return fail(SPGG_E_INVALID, "n_steps must be >= 1");
   int rcode = finish_pending(h);
   if (rcode) return rcode;
+  for (int r = 0; r < h->n_rep; ++r)
+    if (h->stale[r])
+      return fail(SPGG_E_STATE, "replica %d still holds the state of the previous run: give every replica of a "
+                                "batch a state (spgg_set_state / spgg_init_random) before stepping", r);
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream_;
   rcode = ensure_tables(h, n_steps);
@@ -1039,11 +1055,59 @@ extern "C" int spgg_init_random(spgg_t *h, int rep, uint64_t seed) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   h->launches += 1;
-  if (rep == 0) h->iter = 0;
+  begin_new_run(h, rep);
   h->eps_cur[rep] = h->params[rep].epsilon;
   int stop = -1;
   h->stop_at[rep] = -1;
   CUDA_TRY(cudaMemcpy(h->d_stop + rep, &stop, sizeof(int), cudaMemcpyHostToDevice));
+  return SPGG_OK;
+}
+
+// ---------------------------------------------------------------- checkpoint / digests
+extern "C" int spgg_set_progress(spgg_t *h, int64_t iteration, const double *epsilon) {
+  if (!h || !epsilon) return fail(SPGG_E_INVALID, "spgg_set_progress: null argument");
+  if (iteration < 0 || iteration > 0x7fffffff - (1 << 20))
+    return fail(SPGG_E_INVALID, "iteration %lld outside the 31-bit Philox counter word", (long long)iteration);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  for (int r = 0; r < h->n_rep; ++r) {
+    if (h->stale[r]) return fail(SPGG_E_STATE, "replica %d has no state of the run being resumed", r);
+    if (!(epsilon[r] >= 0.0 && epsilon[r] <= 1.0)) return fail(SPGG_E_INVALID, "epsilon[%d] = %g outside [0, 1]", r, epsilon[r]);
+  }
+  if (h->iter != 0) return fail(SPGG_E_STATE, "spgg_set_progress follows the state uploads of a resumed run");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->iter = (long long)iteration;
+  h->replay_first = h->iter;
+  for (int r = 0; r < h->n_rep; ++r) {
+    h->eps_cur[r] = epsilon[r];
+    if (h->stop_at[r] >= 0) h->stop_at[r] = h->iter;  // uniform lattice uploaded: iteration iter+1 breaks
+  }
+  std::vector<int> stop(h->stop_at.begin(), h->stop_at.end());
+  CUDA_TRY(cudaMemcpy(h->d_stop, stop.data(), sizeof(int) * h->n_rep, cudaMemcpyHostToDevice));
+  return SPGG_OK;
+}
+
+extern "C" int spgg_state_digest(spgg_t *h, int rep, uint64_t out[3]) {
+  if (!h || !out) return fail(SPGG_E_INVALID, "spgg_state_digest: null argument");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  unsigned long long *d_out = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_out, 3 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d_out, 0, 3 * sizeof(unsigned long long)));
+  const int grid = 148 * 8;
+  const double rq = h->rc_host[rep].rq;
+#define DIGEST(Md) k_state_digest<Md><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], h->nq(), rq, d_out)
+  if (h->mode == MODE_F32_I8) DIGEST(ModeF32I8);
+  else if (h->mode == MODE_F32_F) DIGEST(ModeF32F);
+  else DIGEST(ModeF64);
+#undef DIGEST
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(SPGG_E_CUDA, "spgg_state_digest: %s", cudaGetErrorString(e));
+  h->launches += 1;
   return SPGG_OK;
 }
 

@@ -1226,4 +1226,49 @@ __global__ void k_export_rows(Geom g, int rep, int i0, int nrows, uint8_t *S, do
   }
 }
 
+// Position-keyed digests of one replica's owned rows: out[0] strategies, out[1] reputations,
+// out[2] Q.  Every site contributes hash(global row, column[, entry]) * (value bits + 1) modulo
+// 2^64, so the digests of the strips of a lattice ADD UP to the digest of the whole lattice:
+// an N-strip run is compared with a single-handle run without moving either state to the host.
+__device__ __forceinline__ unsigned long long digest_mix(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+template <class Md>
+__global__ void k_state_digest(Geom g, int rep, const void *Qd, const void *Rd, const uint32_t *Sd, int nq,
+                               double rq, unsigned long long *out) {
+  typedef typename Md::Q QT;
+  typedef typename Md::R RT;
+  const QT *Qp = reinterpret_cast<const QT *>(Qd) + (long long)rep * g.site_stride * nq;
+  const RT *Rp = reinterpret_cast<const RT *>(Rd) + (long long)rep * g.plane_stride;
+  const uint32_t *Sp = Sd + (long long)rep * g.bits_stride;
+  unsigned long long dS = 0, dR = 0, dQ = 0;
+  const long long n = g.site_stride;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / g.L), col = (int)(e % g.L);
+    const unsigned long long key = ((unsigned long long)(unsigned)(g.row0 + i) << 32) | (unsigned)col;
+    const unsigned long long hS = digest_mix(key * 3 + 1), hR = digest_mix(key * 3 + 2);
+    const unsigned bit = (Sp[(long long)(i + GH) * g.pitchW + WPAD + (col >> 5)] >> (col & 31)) & 1u;
+    dS += hS * (unsigned long long)(bit + 1u);
+    double rv = (double)Rp[(long long)(i + GH) * g.pitchB + CPAD + col];
+    if (sizeof(RT) == 1) rv *= rq;  // int8 units -> the reference's value
+    dR += hR * ((unsigned long long)__double_as_longlong(rv) + 1ull);
+    for (int z = 0; z < nq; ++z) {
+      const double qv = (double)Qp[e * nq + z];
+      dQ += digest_mix(key * 3 + 3 + ((unsigned long long)(z + 1) << 58)) * ((unsigned long long)__double_as_longlong(qv) + 1ull);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    dS += __shfl_down_sync(0xffffffffu, dS, o);
+    dR += __shfl_down_sync(0xffffffffu, dR, o);
+    dQ += __shfl_down_sync(0xffffffffu, dQ, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, dS);
+    atomicAdd(out + 1, dR);
+    atomicAdd(out + 2, dQ);
+  }
+}
+
 }  // namespace spgg

@@ -119,6 +119,36 @@ class Engine:
             Q = Q.reshape((self.rows, self.L, 2, 2) if self.nq == 4 else (self.rows, self.L, 2, 2, 2))
         return S, R, Q
 
+    # -- checkpoint / resume (include/spgg.h: spgg_set_progress)
+    def set_progress(self, iteration: int, epsilons):
+        """Continue a run: the states just uploaded are those after ``iteration`` completed
+        iterations with exploration rates ``epsilons`` (one per replica)."""
+        eps = np.ascontiguousarray(np.atleast_1d(np.asarray(epsilons, dtype=np.float64)))
+        if eps.size != self.n_replicas:
+            raise ValueError(f"need one epsilon per replica ({self.n_replicas}), got {eps.size}")
+        L_.check(self.lib.spgg_set_progress(self._h, int(iteration), eps.ctypes.data))
+
+    def checkpoint(self) -> dict:
+        """Everything a later process needs to continue this run bit for bit: S, R, Q of every
+        replica, the iteration counter and the exploration rates."""
+        st = [self.status(r) for r in range(self.n_replicas)]
+        states = [self.get_state(r) for r in range(self.n_replicas)]
+        return {"iteration": int(max(s.iteration for s in st)), "epsilon": [float(s.epsilon) for s in st],
+                "S": [s[0] for s in states], "R": [s[1] for s in states], "Q": [s[2] for s in states]}
+
+    def restore(self, ck: dict):
+        """Upload a ``checkpoint()`` into this (fresh) handle and continue from its iteration."""
+        for r in range(self.n_replicas):
+            self.set_state(ck["S"][r], ck["R"][r], ck["Q"][r], replica=r)
+        self.set_progress(ck["iteration"], ck["epsilon"])
+
+    def digest(self, replica: int = 0) -> tuple[int, int, int]:
+        """Position-keyed 64-bit digests (S, R, Q) of the owned rows; strips of one lattice add up
+        (mod 2^64) to the digest of the whole lattice (include/spgg.h: spgg_state_digest)."""
+        out = (C.c_uint64 * 3)()
+        L_.check(self.lib.spgg_state_digest(self._h, replica, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def set_replay(self, u, b):
         """``u`` (n,rows,L) float64 and ``b`` (n,rows,L) 0/1: the reference's draw
         arrays for the next n iterations (algorithms.py:105,108)."""

@@ -68,6 +68,15 @@ BAND_CASES = {
                state_representation="action"),
 }
 
+# long-run band ("long-run" means more than 10^3 iterations): the default_config.yaml
+# lattice (L=100) for 10^4 iterations, curves stored at every 10th iteration
+LONG_BAND_CASES = {
+    "c1_long": dict(RUNNER_FIXED, L=100, iterations=10000, r=3.0, influence_factor=1.0,
+                    use_second_order=False, reward_weight_payoff=0.95, rep_gain_C=1.0,
+                    state_representation="reputation"),
+}
+LONG_STRIDE = 10
+
 KEEP_DATASETS = (
     "coop_rate_history", "it_records_final", "rep_avg_history_final", "epsilon_history_final",
     "switch_C_to_D", "switch_D_to_C", "neighbor_influence_percent",
@@ -145,16 +154,20 @@ def _band_worker(args):
     return name, seed, out["datasets"]["coop_rate_history"]
 
 
-def make_bands(n_seeds, procs):
-    jobs = [(name, p, 1000 + s) for name, p in BAND_CASES.items() for s in range(n_seeds)]
+def make_bands(n_seeds, procs, cases=None, stride=1):
+    cases = BAND_CASES if cases is None else cases
+    jobs = [(name, p, 1000 + s) for name, p in cases.items() for s in range(n_seeds)]
     with mp.Pool(procs) as pool:
         res = pool.map(_band_worker, jobs)
-    for name, p in BAND_CASES.items():
-        curves = np.stack([c for (n, s, c) in res if n == name])
+    for name, p in cases.items():
+        curves = np.stack([c for (n, s, c) in res if n == name])[:, ::stride]
         seeds = np.array([s for (n, s, c) in res if n == name])
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"band_{name}.npz"),
-                            params_json=np.array(json.dumps(p)), seeds=seeds,
+                            params_json=np.array(json.dumps(p)), seeds=seeds, stride=np.array(stride),
                             coop_rate_history=curves.astype(np.float32))
+        if stride != 1:
+            print(name, "f_c at the last stored iteration: mean", curves[:, -1].mean(), "sd", curves[:, -1].std())
+            continue
         print(name, "f_c(t=10,100,300,1000) mean",
               curves[:, [9, 99, 299, 999]].mean(0), "sd", curves[:, [9, 99, 299, 999]].std(0))
 
@@ -164,10 +177,15 @@ def main():
     ap.add_argument("--no-band", action="store_true")
     ap.add_argument("--no-replay", action="store_true")
     ap.add_argument("--td", action="store_true", help="also (re)write the SARSA / Expected-SARSA fixtures")
+    ap.add_argument("--long-band", action="store_true",
+                    help="only (re)write the 10^4-iteration band of the default_config.yaml lattice")
     ap.add_argument("--seeds", type=int, default=8)
     ap.add_argument("--procs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
     a = ap.parse_args()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if a.long_band:
+        make_bands(a.seeds, a.procs, LONG_BAND_CASES, LONG_STRIDE)
+        return
     if not a.no_replay:
         for i, (name, p) in enumerate(REPLAY_CASES.items()):
             print("wrote", make_replay(name, p, 7 + i))

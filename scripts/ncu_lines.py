@@ -33,9 +33,9 @@ cur = None
 for l in dis[start + 1:]:
     if l.startswith(".text.") or l.startswith("\t.section"):
         break
-    m = re.search(r'//## File ".*?", line (\d+)', l)
+    m = re.search(r'//## File "(.*?)", line (\d+)', l)
     if m:
-        cur = int(m.group(1))
+        cur = (os.path.basename(m.group(1)), int(m.group(2)), m.group(1))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
@@ -52,7 +52,15 @@ ci, si = h.index("Instructions Executed"), h.index("# Samples")
 print(f"sass instrs: ncu={len(body)} nvdisasm={len(lines)}")
 n = min(len(body), len(lines))
 agg = {}
-src = open([l for l in dis[start:start + 50] if "//## File" in l][0].split('"')[1]).read().splitlines()
+srcs = {}
+def src_line(key):
+    if not key: return "?"
+    b, ln, path = key
+    if path not in srcs:
+        try: srcs[path] = open(path).read().splitlines()
+        except OSError: srcs[path] = []
+    t = srcs[path]
+    return t[ln - 1].strip()[:90] if ln <= len(t) else "?"
 tot_i = tot_s = 0
 for k in range(n):
     ln = lines[k][0]
@@ -62,5 +70,6 @@ for k in range(n):
     tot_i += ie; tot_s += sa
 print(f"total warp-instructions {tot_i}, samples {tot_s}")
 for ln, (ie, sa, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    text = src[ln - 1].strip()[:100] if ln and ln <= len(src) else "?"
-    print(f"{ln:5d} inst={100 * ie / tot_i:5.1f}% samp={100 * sa / max(1, tot_s):5.1f}% sass={cnt:4d}  {text}")
+    ln_key = ln
+    text = src_line(ln)
+    print(f"{(ln[0][:14] if ln else '?'):14s}:{(ln[1] if ln else 0):5d} inst={100 * ie / tot_i:5.1f}% samp={100 * sa / max(1, tot_s):5.1f}% sass={cnt:4d}  {text}")

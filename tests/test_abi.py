@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_error_string():
     import spgg_b200
     lib = spgg_b200.load()
-    assert lib.spgg_abi_version() == 1
+    assert lib.spgg_abi_version() == 2
     assert isinstance(lib.spgg_last_error(), bytes)
 
 

@@ -304,23 +304,35 @@ def test_early_exit_matches_reference_semantics():
     eng.close(); eng2.close()
 
 
-def test_L4096_two_steps_vs_oracle_and_invariants():
-    """BASELINE config 4 size: bit-exact against the oracle for two iterations, then
+def test_L4096_32_iterations_vs_oracle_and_invariants():
+    """BASELINE config 4, the geometry bench.py times (32 x 256 tiles of 128 x 16 sites walked by
+    296 persistent CTAs): 32 iterations fp32 / Philox against the C oracle, S, R, Q and the integer
+    statistics bit for bit.  32 iterations take the reputations into both clamps (|R| = 10 needs
+    10), move epsilon through 32 thresholds and make every CTA walk its whole tile list; then
     size-independent invariants over a longer run."""
     from oracle import c_oracle
-    L = 4096
+    L, n = 4096, 32
     p = full_params(dict(C1, L=L))
     rs = np.random.RandomState(2)
     Q0 = rs.uniform(-0.01, 0.01, (L, L, 2, 2)).astype(np.float32).astype(np.float64)
     S0 = rs.randint(0, 2, (L, L)).astype(np.uint8)
     eng = _engine(p, seeds=7, precision="fp32")
+    assert eng.describe().startswith("fast")
     eng.set_state(S0, np.zeros((L, L)), Q0)
-    eng.step(2)
+    eng.step(n)
     S, R, Q = eng.get_state()
+    rows = eng.stats()[1:]
     sim = c_oracle.Sim(p, S0, np.zeros((L, L)), Q0, "fp32", seed=7)
-    sim.run(2)
-    assert np.array_equal(S, sim.S) and np.array_equal(R, sim.R.astype(np.float64))
+    rows_o = sim.run(n)
+    assert np.array_equal(S, sim.S), f"{(S != sim.S).sum()} strategy mismatches"
+    assert np.array_equal(R, sim.R.astype(np.float64))
     assert np.array_equal(Q.astype(np.float32), sim.Q)
+    assert R.min() == p["R_min"] and R.max() == p["R_max"]       # both clamps were reached
+    ints = [0, 1, 2, 3, 11, 12, 13, 14, 15, 16, 31, 32]
+    assert np.array_equal(rows[:, ints], rows_o[:, ints])
+    assert np.array_equal(rows[:, 33].astype(np.float32), rows_o[:, 33].astype(np.float32))  # exact max
+    np.testing.assert_allclose(rows[:, 4:11], rows_o[:, 4:11], rtol=1e-5)
+    np.testing.assert_allclose(rows[:, 18:31], rows_o[:, 18:31], rtol=2e-4, atol=1e-2)
     eng.step(40)
     rows = eng.stats()
     it = rows[1:]

@@ -108,6 +108,39 @@ def test_philox_stream_stays_in_the_reference_seed_band(golden_dir, cfg):
         eng.close()
 
 
+def test_philox_long_run_stays_in_the_reference_seed_band(golden_dir):
+    """north_star "long-run": the default_config.yaml lattice (L=100, C1 physics) for 10^4
+    iterations, 8 Philox seeds against the band of 8 runs of the executed reference
+    (tests/golden/band_c1_long.npz, every 10th entry of coop_rate_history).  Checked: the curve at
+    t = 10^3, 3*10^3, 9990 within mean +- max(4 sd, 0.02), and the time average over the last 2000
+    iterations (every 10th) within mean +- max(4 sd, 0.01) of the reference's."""
+    import spgg_b200
+    z = np.load(os.path.join(golden_dir, "band_c1_long.npz"))
+    p = json.loads(str(z["params_json"]))
+    stride = int(z["stride"])
+    curves = z["coop_rate_history"].astype(np.float64)       # (seeds, T/stride)
+    mean, sd = curves.mean(0), curves.std(0)
+    T, L = p["iterations"], p["L"]
+    tail_ref = curves[:, -2000 // stride:].mean(1)
+    tails = []
+    for seed in range(11, 19):
+        eng = spgg_b200.Engine(p, seeds=seed, precision="fp32")
+        rs = np.random.RandomState(seed)
+        eng.set_state(rs.randint(0, 2, (L, L)), np.zeros((L, L)), rs.uniform(-0.01, 0.01, (L, L, 2, 2)))
+        eng.step(T)
+        rows = eng.stats()
+        # coop_rate_history[t] = cooperators of S_t (spgg.py:383): column NC_OLD of iteration t+1
+        fc = rows[1:, 0] / (L * L)
+        assert len(fc) == T == curves.shape[1] * stride
+        for t in (1000, 3000, 9990):
+            tol = max(4 * sd[t // stride], 0.02)
+            assert abs(fc[t] - mean[t // stride]) <= tol, (seed, t, fc[t], mean[t // stride], sd[t // stride])
+        tails.append(fc[-2000::stride].mean())
+        eng.close()
+    tol = max(4 * tail_ref.std(), 0.01)
+    assert abs(np.mean(tails) - tail_ref.mean()) <= tol, (np.mean(tails), tail_ref.mean(), tail_ref.std())
+
+
 def test_foreign_algorithm_subclass_fails_loudly(tmp_path):
     """The reference accepts any RLAlgorithm instance (spgg.py:115-116); a rule that is not one of
     its four cannot run inside the fused kernel and must say so (no CPU fallback)."""

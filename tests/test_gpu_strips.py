@@ -19,9 +19,12 @@ def _ngpu():
     ("fp32", 1, "action", 256, 4),
     ("fp32", 1, "reputation", 100, 3),      # general path, ragged strips
     ("fp64", 0, "reputation", 64, 2),
+    # the benchmarked tile geometry: n_tx = 32 tile columns, 2048-row strips, every persistent CTA
+    # walks several tiles and the strip's own top / bottom tiles take the ghost-row path
+    ("fp32", 0, "reputation", 4096, 2),
 ])
 def test_strips_equal_single_lattice_gloo(precision, second, state, L, world):
-    res = launch_ranks(["gpu", "gloo", precision, second, state, L, 12], world, timeout=600)
+    res = launch_ranks(["gpu", "gloo", precision, second, state, L, 12], world, timeout=900)
     for rc, out in res:
         assert rc == 0, out
 
@@ -29,6 +32,7 @@ def test_strips_equal_single_lattice_gloo(precision, second, state, L, world):
 @pytest.mark.parametrize("precision,second,state,L", [
     ("fp32", 0, "reputation", 512),
     ("fp32", 1, "reputation", 384),
+    ("fp32", 0, "reputation", 4096),
 ])
 def test_strips_equal_single_lattice_nccl(precision, second, state, L):
     n = _ngpu()
