@@ -98,9 +98,38 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline_numpy(L, iters, seed=0):
-    """The reference's NumPy path restated (oracle/spgg_numpy.py, pinned bit-exact to the
-    reference), timed on this host.  Returns site-updates/s."""
+def c4_config(L, inner):
+    """`config` of the N=1 line (both arms print the same one)."""
+    return {"workload": f"C4: single lattice L={L}, reputation state, M=1, r=3, kappa=1, "
+                        f"w_P=0.95, Q-learning; {inner} iterations per bench step, "
+                        "statistics on, Philox draws",
+            "L": L, "iterations_per_step": inner, "precision": "fp32 Q (float4) + int8 R + bit S",
+            "l2": f"state {state_bytes_dev(L) / 1e6:.0f} MB per pass > 126 MB L2 (no flush needed)",
+            "e2e_def": "SPGG C-ABI with host buffers: ONE set_state (H2D of uint8 S, f64 R, f64 Q) + "
+                       "K chunks with the stat rows read back each chunk + ONE get_state (D2H), all "
+                       "inside the timed region; the simulation is device-resident, so the state "
+                       "transfers are amortised over the K x iterations_per_step iterations of the run"}
+
+
+def reference_root():
+    """The unmodified reference: /root/reference in the build container, oracle/_ref (shipped by
+    oracle/fetch_ref.py) on the GPU box, else None."""
+    from oracle import fetch_ref
+    return fetch_ref.reference_root()
+
+
+def cpu_reference(L, n_warm, n_timed):
+    """The UNMODIFIED reference (`SPGG.run`, NumPy, one process: its ops are single-threaded)
+    timed on this host; h5py / matplotlib stubbed (absent from the image), `label` neutralised
+    for L > 1000.  Returns (site-updates/s, seconds per iteration)."""
+    from oracle import ref_harness
+    sec, _iv = ref_harness.time_reference(n_warm, n_timed, seed=0, L=L, **C4)
+    return L * L / sec, sec
+
+
+def cpu_port(L, iters, seed=0):
+    """Fallback when no copy of the reference is present: its NumPy path restated
+    (oracle/spgg_numpy.py, pinned bit-exact to the reference).  Returns (site-updates/s, s)."""
     from oracle import spgg_numpy
     p = dict(C4, L=L, iterations=iters)
     rs = np.random.RandomState(seed)
@@ -115,49 +144,45 @@ def cpu_baseline_numpy(L, iters, seed=0):
         S, R, Q, _st = spgg_numpy.qlearning_step(S, R, Q, eps, u, b, p)
         eps = max(eps * p["epsilon_decay"], p["epsilon_min"])
     dt = time.perf_counter() - t0
-    return L * L * iters / dt, dt
+    return L * L * iters / dt, dt / iters
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the reference's CPU implementation of the path.  The reference is
-    pure Python and cannot travel to the GPU box (and may not be copied), so this is its
-    NumPy restatement (oracle port, bit-exact to it), single process like the reference's
-    own loop (its NumPy ops are single-threaded)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host
+    cores - the UNMODIFIED reference tree (oracle/_ref, shipped by oracle/fetch_ref.py) run
+    through its public `SPGG(**params).run(h5)`; when no copy is present, its NumPy restatement
+    (oracle port).  One process: the reference's per-lattice loop is single-threaded NumPy (its
+    only parallelism is one process per parameter tuple, runner.py:142, and C4 is one lattice).
+    A bench step here is ONE iteration of a bounded sample lattice of the C4 physics, sized so
+    that the K + W iterations end within a few minutes (the full L=4096 lattice when they fit:
+    about 27 s per iteration)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    # bounded sample: one iteration of an Ls x Ls lattice per step, ~100 M site-updates in all
-    budget_sites = 9.0e7
-    Ls = int(min(4096, max(128, (budget_sites / max(1, steps + warm)) ** 0.5)))
-    Ls -= Ls % 32
-    from oracle import spgg_numpy
-    p = dict(C4, L=Ls)
-    rs = np.random.RandomState(0)
-    Q = rs.uniform(-0.01, 0.01, (Ls, Ls, 2, 2))
-    S = rs.randint(0, 2, (Ls, Ls)).astype(np.int64)
-    R = np.zeros((Ls, Ls))
-    eps = p["epsilon"]
-    t_timed = 0.0
-    for it in range(warm + steps):
-        u = rs.rand(Ls, Ls)
-        b = rs.randint(0, 2, (Ls, Ls))
-        t0 = time.perf_counter()
-        S, R, Q, _ = spgg_numpy.qlearning_step(S, R, Q, eps, u, b, p)
-        dt = time.perf_counter() - t0
-        eps = max(eps * p["epsilon_decay"], p["epsilon_min"])
-        if it >= warm:
-            t_timed += dt
-    value = Ls * Ls * steps / t_timed
-    sample = f"{steps} iterations of an L={Ls} lattice (same physics as the L=4096 workload)"
+    L_full = args.L or 4096
+    budget_s, rate = 150.0, 0.7e6           # ~0.6-1.2 M site-updates/s measured in the survey
+    Ls = int(min(L_full, (budget_s * rate / max(1, steps + warm)) ** 0.5))
+    Ls = max(128, Ls - Ls % 32)
+    root = reference_root()
+    if root is not None:
+        value, sec = cpu_reference(Ls, warm, steps)
+        kind = "reference"
+        how = f"unmodified reference ({'oracle/_ref' if 'oracle' in root else root}), SPGG.run"
+    else:
+        value, sec = cpu_port(Ls, warm + steps)
+        kind = "port"
+        how = "NumPy restatement of the reference loop (oracle/spgg_numpy.py)"
+    sample = (f"{steps} timed iterations of an L={Ls} lattice with the C4 physics "
+              f"({'the full workload lattice' if Ls == L_full else f'bounded sample of the L={L_full} workload'}), "
+              f"{how}, 1 process")
     line = {
         "impl": "reference", "metric": "site-updates/s", "value": value, "unit": "site-updates/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": 1e3 * t_timed / steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4 physics: reputation state, M=1, r=3, kappa=1, w_P=0.95 "
-                               f"(reference NumPy path restated; sample lattice L={Ls})"},
-        "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": 1, "kind": "port",
+        "config": c4_config(L_full, args.inner),
+        "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": 1, "kind": kind,
                          "sample": sample, "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -296,23 +321,24 @@ def main():
     # ---------------- CPU baseline beside it (bounded sample)
     cpu = None
     if not args.no_cpu_baseline:
-        v, dt = cpu_baseline_numpy(args.cpu_L, 1)
-        cpu = {"value": v, "unit": "site-updates/s", "cores": 1, "kind": "port",
-               "sample": f"1 iteration of the L={args.cpu_L} lattice with the NumPy restatement of the "
-                         f"reference path ({dt:.1f} s)", "host_cpus": os.cpu_count()}
+        if reference_root() is not None:
+            v, dt = cpu_reference(args.cpu_L, 1, 1)
+            cpu = {"value": v, "unit": "site-updates/s", "cores": 1, "kind": "reference",
+                   "sample": f"1 timed iteration (after 1 warm-up iteration) of the L={args.cpu_L} lattice, C4 "
+                             f"physics, with the unmodified reference's SPGG.run ({dt:.1f} s per iteration)",
+                   "host_cpus": os.cpu_count()}
+        else:
+            v, dt = cpu_port(args.cpu_L, 1)
+            cpu = {"value": v, "unit": "site-updates/s", "cores": 1, "kind": "port",
+                   "sample": f"1 iteration of the L={args.cpu_L} lattice with the NumPy restatement of the "
+                             f"reference path ({dt:.1f} s); no copy of the reference on this box",
+                   "host_cpus": os.cpu_count()}
 
     line = {
         "metric": "site-updates/s", "value": value, "unit": "site-updates/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C4: single lattice L={L}, reputation state, M=1, r=3, kappa=1, "
-                               f"w_P=0.95, Q-learning; {inner} iterations per bench step, "
-                               "statistics on, Philox draws",
-                   "L": L, "iterations_per_step": inner, "precision": "fp32 Q (float4) + int8 R + bit S",
-                   "l2": f"state {state_bytes_dev(L) / 1e6:.0f} MB per pass > 126 MB L2 (no flush needed)",
-                   "e2e_def": "SPGG C-ABI with host buffers: set_state (H2D of uint8 S, f64 R, f64 Q) + "
-                              "K chunks with the stat rows read back each chunk + get_state (D2H), "
-                              "all inside the timed region"},
+        "config": c4_config(L, inner),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "site-updates/s",
                 "h2d_bytes_per_step": state_bytes / K, "d2h_bytes_per_step": (state_bytes + d2h_stats) / K,

@@ -29,7 +29,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SPGG_REFERENCE_ROOT", "/root/reference")
+def _find_reference() -> str:
+    # the live tree in the build container, else the copy oracle/fetch_ref.py shipped (GPU box)
+    live = os.environ.get("SPGG_REFERENCE_ROOT", "/root/reference")
+    shipped = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for root in (live, shipped):
+        if os.path.isfile(os.path.join(root, "src", "model", "spgg.py")):
+            return root
+    return live
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:
@@ -209,3 +219,42 @@ def run_reference(seed: int, cluster_tail: bool = True, **params):
         out["b"] = (np.stack(log["randint"]).astype(np.uint8) if n_steps
                     else np.zeros((0, L, L), np.uint8))
     return out
+
+
+def time_reference(n_warm: int, n_timed: int, seed: int = 0, **params):
+    """Wall time per iteration of the UNMODIFIED reference loop (``spgg.py:368-592``) on this
+    host: one ``SPGG.run`` of ``n_warm + n_timed`` iterations; the boundaries between iterations
+    are observed through the one public hook the loop calls exactly once per iteration,
+    ``algorithm.decay_epsilon`` (``spgg.py:548-550``), so each interval covers one whole loop
+    body.  ``label`` is neutralised for L > 1000 (the O(#clusters L^2)
+    tail ``spgg.py:631-633`` is not part of the step).  Returns (seconds per timed iteration,
+    list of the timed intervals)."""
+    import time
+
+    ref_model = import_reference()
+    if int(params.get("L", 50)) > 1000:
+        neutralise_cluster_tail()
+    params = dict(params, iterations=int(n_warm + n_timed))
+    with pinned_seed(seed):
+        model = ref_model.SPGG(**params)
+    tmp = tempfile.mkdtemp(prefix="spgg_ref_")
+    model.folder = tmp
+    stamps = []
+    real_decay = model.algorithm.decay_epsilon
+
+    def decay_and_stamp(*a, **k):
+        out = real_decay(*a, **k)
+        stamps.append(time.perf_counter())
+        return out
+
+    model.algorithm.decay_epsilon = decay_and_stamp
+    t_start = time.perf_counter()
+    fname = os.path.join(tmp, "run.h5")
+    model.run(fname)
+    _RecordingFile.store.pop(fname, None)
+    stamps = [t_start] + stamps
+    iv = [b - a for a, b in zip(stamps[:-1], stamps[1:])]
+    timed = iv[n_warm:n_warm + n_timed]
+    if len(timed) < n_timed:      # the lattice became uniform (spgg.py:405): fewer iterations ran
+        timed = iv[-max(1, len(iv) - n_warm):]
+    return sum(timed) / len(timed), timed
