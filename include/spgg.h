@@ -105,6 +105,8 @@ typedef struct spgg_status {
   int32_t n_replicas;
   int32_t r_is_int8;
   int64_t kernel_launches; /* kernels launched by this handle so far                 */
+  int64_t speculative_launches; /* update launches that guessed the global maximum (below) */
+  int64_t speculation_failures; /* ... whose guess was wrong: that iteration and the rest of its chunk were re-run */
 } spgg_status_t;
 
 typedef struct spgg_handle spgg_t;
@@ -168,7 +170,14 @@ int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const double *u, 
 /* Run n_steps iterations of the loop body spgg.py:368-592 for all replicas
  * (asynchronous on `cuda_stream`, a cudaStream_t or NULL).  One launch for the
  * whole call when the lattices fit in shared memory (one thread-block cluster
- * per replica, csrc/spgg_resident.cuh), two launches per iteration otherwise. */
+ * per replica, csrc/spgg_resident.cuh); otherwise per iteration either the exact
+ * pair k_gmax (lattice-global max |reward difference|, spgg.py:488) + k_step, or -
+ * TMA fast path - ONE launch that assumes the maximum of the previous iteration,
+ * computes the true one as a by-product of the update and compares.  A wrong guess
+ * is caught on the device (every later launch of the call returns untouched) and the
+ * call is re-run from that iteration by the next synchronising entry point with the
+ * value now known, so results never depend on the guess (Q is a ping-pong pair on
+ * such handles).  SPGG_NO_SPEC=1 in the environment keeps the exact pair. */
 int spgg_step(spgg_t *h, int n_steps, void *cuda_stream);
 int spgg_sync(spgg_t *h);
 
@@ -196,6 +205,9 @@ int spgg_halo_unpack(spgg_t *h, const void *dev_from_up, const void *dev_from_do
  * value at spgg_gmax_device_ptr(), repeat. */
 int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *cuda_stream);
 int spgg_phase_gmax(spgg_t *h, void *cuda_stream);
+/* One whole iteration inside begin/end: what spgg_step does per iteration (a single
+ * speculative launch when the handle can guess the maximum, else k_gmax + k_step). */
+int spgg_phase_iteration(spgg_t *h, int do_select, void *cuda_stream);
 void *spgg_gmax_device_ptr(spgg_t *h);
 int spgg_begin_steps(spgg_t *h, int n_steps, void *cuda_stream);
 int spgg_end_steps(spgg_t *h, void *cuda_stream);

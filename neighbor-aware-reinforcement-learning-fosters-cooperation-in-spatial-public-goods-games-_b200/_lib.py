@@ -48,7 +48,8 @@ class Status(C.Structure):
     """``spgg_status_t``"""
     _fields_ = [("iteration", C.c_int64), ("stopped_at", C.c_int64), ("epsilon", C.c_double),
                 ("n_replicas", C.c_int32), ("r_is_int8", C.c_int32),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("speculative_launches", C.c_int64),
+                ("speculation_failures", C.c_int64)]
 
 
 EXPORTS = (
@@ -58,7 +59,7 @@ EXPORTS = (
     "spgg_halo_pack", "spgg_halo_unpack", "spgg_phase_kernel", "spgg_phase_gmax",
     "spgg_gmax_device_ptr", "spgg_begin_steps", "spgg_end_steps", "spgg_last_error",
     "spgg_abi_version", "spgg_init_random", "spgg_describe", "spgg_set_progress",
-    "spgg_state_digest",
+    "spgg_state_digest", "spgg_phase_iteration",
 )
 
 _lib = None
@@ -92,6 +93,7 @@ def load():
     lib.spgg_halo_unpack.argtypes = [vp, vp, vp, vp]
     lib.spgg_phase_kernel.argtypes = [vp, i32, i32, vp]
     lib.spgg_phase_gmax.argtypes = [vp, vp]
+    lib.spgg_phase_iteration.argtypes = [vp, i32, vp]
     lib.spgg_gmax_device_ptr.argtypes = [vp]
     lib.spgg_gmax_device_ptr.restype = vp
     lib.spgg_begin_steps.argtypes = [vp, i32, vp]

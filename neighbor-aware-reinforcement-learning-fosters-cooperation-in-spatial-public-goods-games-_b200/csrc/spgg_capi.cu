@@ -55,7 +55,21 @@ struct spgg_handle {
   size_t smem_step = 0, smem_gmax = 0;
   // device memory
   RepConst *d_rc = nullptr;
-  void *d_Q = nullptr;
+  void *d_Qb[2] = {nullptr, nullptr};  // [1] only with spec: Q is then read from [qcur] and written to [qcur^1]
+  int qcur = 0;
+  void *Qcur() const { return d_Qb[qcur]; }
+  // speculative global maximum (KArgs::spec): fast path only; SPGG_NO_SPEC=1 keeps the exact two-launch iteration
+  bool spec = false;
+  bool carry_valid = false;   // gcarry holds the maximum of the iteration before the next update launch
+  float *d_gcarry = nullptr;
+  int *d_bad = nullptr;
+  CUtensorMap qmaps[2];
+  bool spec_on = true;            // switched off for good when the maximum changes too often to be worth guessing
+  long long spec_launches = 0, spec_failures = 0;
+  long long spec_iterations = 0;  // iterations finished by launches that guessed (re-runs not counted twice)
+  bool in_rerun = false;
+  int pend_qcur0 = 0;
+  std::vector<char> pend_cur_after, pend_q_after;  // plane / Q parity after the launch with relative index rel
   void *d_R[2] = {nullptr, nullptr};
   void *d_code[2] = {nullptr, nullptr};
   uint32_t *d_S[2] = {nullptr, nullptr};
@@ -313,7 +327,7 @@ extern "C" int spgg_abi_version(void) { return SPGG_ABI_VERSION; }
 extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
 
 static int free_all(spgg_handle *h) {
-  cudaFree(h->d_rc); cudaFree(h->d_Q);
+  cudaFree(h->d_rc); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_R[i]); cudaFree(h->d_code[i]); cudaFree(h->d_S[i]); }
   cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_partials); cudaFree(h->d_tickets);
   cudaFree(h->d_stop); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_u); cudaFree(h->d_b);
@@ -498,6 +512,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   g.ctas_per_rep = (int)std::min<long long>(n_tiles, per_rep);
   // the fast kernel's packed 16-bit counters bound the sites one thread may visit per launch
   if (h->fast && (g.site_stride / ((long long)g.ctas_per_rep * FTHREADS)) > 60000) h->fast = false;
+  h->spec = h->fast && getenv("SPGG_NO_SPEC") == nullptr;
 
   const size_t nQ = (size_t)n_replicas * g.site_stride * h->nq() * h->elem_Q();
   const size_t nR = (size_t)n_replicas * g.plane_stride * h->elem_R();
@@ -513,7 +528,8 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     cudaMemset((ptr), 0, (bytes));                                                          \
   } while (0)
   ALLOC(h->d_rc, sizeof(RepConst) * n_replicas);
-  ALLOC(h->d_Q, nQ);
+  ALLOC(h->d_Qb[0], nQ);
+  if (h->spec) { ALLOC(h->d_Qb[1], nQ); ALLOC(h->d_gcarry, sizeof(float) * n_replicas); ALLOC(h->d_bad, sizeof(int)); }
   for (int i = 0; i < 2; ++i) { ALLOC(h->d_R[i], nR); ALLOC(h->d_code[i], nC); ALLOC(h->d_S[i], nS); }
   ALLOC(h->d_partials, sizeof(double) * (size_t)n_replicas * g.ctas_per_rep * NSTAT);
   ALLOC(h->d_tickets, sizeof(unsigned) * n_replicas);
@@ -534,13 +550,17 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
       if (!e) e = make_map(&fm.st_code, h->d_code[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
       if (!e) e = make_map(&fm.st_R, h->d_R[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
       if (!e) e = make_map(&fm.st_S, h->d_S[i ^ 1], (uint64_t)g.pitchW * 4, nrows, n_replicas, (uint64_t)g.bits_stride * 4, TC / 8, FTR);
-      if (!e) e = make_map_q(&fm.q, h->d_Q, (uint64_t)g.L, (uint64_t)g.rows, (uint64_t)n_replicas);
+      if (!e) e = make_map_q(&h->qmaps[i], h->d_Qb[(i == 1 && h->spec) ? 1 : 0], (uint64_t)g.L, (uint64_t)g.rows, (uint64_t)n_replicas);
       if (e) { free_all(h); delete h; return e; }
     }
   }
   CUDA_TRY(cudaMemcpy(h->d_rc, h->rc_host.data(), sizeof(RepConst) * n_replicas, cudaMemcpyHostToDevice));
   std::vector<int> neg(n_replicas, -1);
   CUDA_TRY(cudaMemcpy(h->d_stop, neg.data(), sizeof(int) * n_replicas, cudaMemcpyHostToDevice));
+  if (h->spec) {
+    const int none = 0x7fffffff;
+    CUDA_TRY(cudaMemcpy(h->d_bad, &none, sizeof(int), cudaMemcpyHostToDevice));
+  }
   h->eps_cur.resize(n_replicas);
   for (int r = 0; r < n_replicas; ++r) h->eps_cur[r] = params[r].epsilon;
   h->stop_at.assign(n_replicas, -1);
@@ -550,11 +570,64 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
 }
 
 // ---------------------------------------------------------------- pending chunk
+static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_t st, bool allow_spec);
+
+// A speculative update launch found that the global maximum it assumed was not the one it computed
+// (KArgs::spec): every later launch of the chunk returned without touching anything, so the inputs of
+// the failed launch are intact (planes and Q are ping-pong pairs).  Re-run from there; the failed
+// launch left the exact maximum in gcarry, so the re-run's guess is right.
+static int rerun_failed_speculation(spgg_handle *h) {
+  for (;;) {
+    int bad = 0x7fffffff;
+    CUDA_TRY(cudaMemcpy(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad == 0x7fffffff) return SPGG_OK;
+    if (getenv("SPGG_SPEC_DEBUG")) fprintf(stderr, "[spgg] speculation failed at launch %d of %d (t0 %lld), %lld speculative launches so far\n", bad, h->pend_n, h->pend_t0, h->spec_launches);
+    if (bad < 1 || bad > h->pend_n) return fail(SPGG_E_STATE, "speculation bookkeeping out of range (%d of %d)", bad, h->pend_n);
+    h->spec_failures += 1;
+    // small lattices change their maximum every few iterations: not worth guessing there
+    if (h->spec_failures > 8 && h->spec_failures * 16 > h->spec_iterations) h->spec_on = false;
+    const int none = 0x7fffffff;
+    CUDA_TRY(cudaMemcpy(h->d_bad, &none, sizeof(int), cudaMemcpyHostToDevice));
+    // a uniform-lattice flag raised by the failed launch itself is not to be trusted
+    std::vector<int> stop(h->n_rep);
+    CUDA_TRY(cudaMemcpy(stop.data(), h->d_stop, sizeof(int) * h->n_rep, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < h->n_rep; ++r)
+      if (stop[r] == (int)(h->pend_t0 + bad) + 1) stop[r] = -1;
+    CUDA_TRY(cudaMemcpy(h->d_stop, stop.data(), sizeof(int) * h->n_rep, cudaMemcpyHostToDevice));
+    // parities as launch bad-1 left them
+    h->cur = h->pend_cur_after[bad - 1];
+    h->qcur = h->pend_q_after[bad - 1];
+    h->carry_valid = true;
+    h->pend_rel = bad - 1;
+    h->in_rerun = true;
+    const int n = h->pend_n;
+    for (int s = bad; s <= n; ++s) {
+      h->pend_rel += 1;
+      int rcode = launch_step(h, 1, s < n ? 1 : 0, h->pend_stream, true);
+      if (rcode) return rcode;
+      if (!h->spec_on && s < n) {  // speculation was just switched off: the rest of the chunk runs exactly
+        for (++s; s <= n; ++s) {
+          rcode = spgg_phase_gmax(h, h->pend_stream);
+          if (!rcode) rcode = launch_step(h, 1, s < n ? 1 : 0, h->pend_stream, false);
+          if (rcode) return rcode;
+        }
+      }
+    }
+    h->in_rerun = false;
+    CUDA_TRY(cudaStreamSynchronize(h->pend_stream));
+    CUDA_TRY(cudaGetLastError());
+  }
+}
+
 static int finish_pending(spgg_handle *h) {
   if (!h->pending) return SPGG_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->pend_stream));
   CUDA_TRY(cudaGetLastError());
+  if (h->spec && h->pend_rel == h->pend_n && !h->pend_resident) {
+    int rcode = rerun_failed_speculation(h);
+    if (rcode) return rcode;
+  }
   std::vector<int> stop(h->n_rep);
   CUDA_TRY(cudaMemcpy(stop.data(), h->d_stop, sizeof(int) * h->n_rep, cudaMemcpyDeviceToHost));
   // Replicas stop independently; plane parity is shared, so a stopped replica's planes are
@@ -574,6 +647,7 @@ static int finish_pending(spgg_handle *h) {
     h->pend_resident = false;
   } else if (h->n_rep == 1 && stop[0] >= 0 && stop[0] < t_end) {
     h->cur = h->pend_cur0 ^ (int)((stop[0] - h->pend_t0) & 1);
+    h->qcur = h->pend_q_after[(size_t)(stop[0] - h->pend_t0)];  // the launch that finished iteration stop[0] wrote Q last
     h->iter = stop[0];
   } else {
     if (h->n_rep > 1) {
@@ -588,6 +662,12 @@ static int finish_pending(spgg_handle *h) {
             CUDA_TRY(cudaMemcpy(h->d_S[h->cur] + (size_t)r * g.bits_stride,
                                 h->d_S[src] + (size_t)r * g.bits_stride,
                                 (size_t)g.bits_stride * 4, cudaMemcpyDeviceToDevice));
+          }
+          const int qsrc = h->pend_q_after[(size_t)(stop[r] - h->pend_t0)];
+          if (qsrc != h->qcur) {   // ping-pong Q: the stopped replica's table stayed in the other buffer
+            const size_t qb = (size_t)h->g.site_stride * h->nq() * h->elem_Q();
+            CUDA_TRY(cudaMemcpy((char *)h->d_Qb[h->qcur] + (size_t)r * qb, (char *)h->d_Qb[qsrc] + (size_t)r * qb, qb,
+                                cudaMemcpyDeviceToDevice));
           }
         }
       }
@@ -631,6 +711,7 @@ static void begin_new_run(spgg_handle *h, int rep) {
     std::fill(h->stale.begin(), h->stale.end(), 1);
   }
   h->stale[rep] = 0;
+  h->carry_valid = false;  // the global maximum of the run before says nothing about this one
 }
 
 extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double *R, const double *Q) {
@@ -653,7 +734,7 @@ extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double
     CUDA_TRY(cudaMemcpyAsync(h->d_sc_Q, Q + off * h->nq(), n * h->nq() * sizeof(double), cudaMemcpyHostToDevice, 0));
     const int grid = (int)std::min<long long>(148 * 16, ((long long)nr * ((g.L + 31) / 32) * 32 + 255) / 256);
 #define IMPORT(Md) k_import_rows<Md><<<std::max(1, grid), 256>>>(g, rep, i0, nr, h->d_sc_S, h->d_sc_R, h->d_sc_Q, \
-                       h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->d_sc_info, h->nq())
+                       h->Qcur(), h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->d_sc_info, h->nq())
     if (h->mode == MODE_F32_I8) IMPORT(ModeF32I8);
     else if (h->mode == MODE_F32_F) IMPORT(ModeF32F);
     else IMPORT(ModeF64);
@@ -692,7 +773,7 @@ extern "C" int spgg_get_state(spgg_t *h, int rep, uint8_t *S, double *R, double 
     const size_t n = (size_t)nr * g.L, off = (size_t)i0 * g.L;
     const int grid = (int)std::min<long long>(148 * 16, ((long long)n + 255) / 256);
 #define EXPORT(Md) k_export_rows<Md><<<std::max(1, grid), 256>>>(g, rep, i0, nr, S ? h->d_sc_S : nullptr, \
-                       R ? h->d_sc_R : nullptr, Q ? h->d_sc_Q : nullptr, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->nq())
+                       R ? h->d_sc_R : nullptr, Q ? h->d_sc_Q : nullptr, h->Qcur(), h->d_R[h->cur], h->d_S[h->cur], rc.rq, h->nq())
     if (h->mode == MODE_F32_I8) EXPORT(ModeF32I8);
     else if (h->mode == MODE_F32_F) EXPORT(ModeF32F);
     else EXPORT(ModeF64);
@@ -792,22 +873,34 @@ extern "C" int spgg_begin_steps(spgg_t *h, int n_steps, void *stream_) {
   h->pend_t0 = h->iter;
   h->pend_n = n_steps;
   h->pend_cur0 = h->cur;
+  h->pend_qcur0 = h->qcur;
+  h->pend_cur_after.assign((size_t)n_steps + 1, (char)h->cur);
+  h->pend_q_after.assign((size_t)n_steps + 1, (char)h->qcur);
   h->pend_rel = 0;
   h->pend_stream = st;
   return SPGG_OK;
 }
 
+// does the launch that follows iteration index j (choosing the action of j+1) read replayed draws?
+static bool launch_replays(const spgg_handle *h, long long j, int do_select) {
+  const long long draw = j - h->replay_first;  // draws of iteration j+1 are entry `draw`
+  return do_select && h->d_u && draw >= 0 && draw < h->replay_n;
+}
+// may the update launch that finishes iteration pend_rel+1 guess the global maximum (KArgs::spec)?
+static bool can_speculate(const spgg_handle *h, int do_select) {
+  return h->fast && h->spec && h->spec_on && h->carry_valid &&
+         !launch_replays(h, h->pend_t0 + h->pend_rel + 1, do_select);
+}
+
 // one k_step launch at relative index pend_rel (finishing iteration pend_t0+pend_rel)
-extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *stream_) {
-  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_phase_kernel outside begin/end");
-  cudaStream_t st = (cudaStream_t)stream_;
+static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_t st, bool allow_spec) {
   const long long j = h->pend_t0 + h->pend_rel;
   const long long draw = j - h->replay_first;  // draws of iteration j+1 are entry `draw`
-  const bool replay = do_select && h->d_u && draw >= 0 && draw < h->replay_n;
+  const bool replay = launch_replays(h, j, do_select);
   KArgs a;
   a.g = h->g;
   a.rc = h->d_rc;
-  a.Q = h->d_Q;
+  a.Q = h->Qcur();
   a.R_in = h->d_R[h->cur]; a.R_out = h->d_R[h->cur ^ 1];
   a.code_in = h->d_code[h->cur]; a.code_out = h->d_code[h->cur ^ 1];
   a.S_in = h->d_S[h->cur]; a.S_out = h->d_S[h->cur ^ 1];
@@ -827,6 +920,13 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   a.b3 = (upd_replay && np_ == 3) ? h->d_b + ((size_t)ue * 3 + 2) * ss : nullptr;
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
+  const bool use_fast = h->fast && !replay;
+  a.spec = 0; a.gcarry = nullptr; a.bad_at = nullptr;
+  if (use_fast && h->spec) {
+    a.gcarry = h->d_gcarry;
+    a.bad_at = h->d_bad;
+    a.spec = (allow_spec && do_update && h->spec_on && h->carry_valid) ? 1 : 0;
+  }
 #ifdef SPGG_TRACE
   {  // debug builds only: dump the per-CTA timeline of the previous fused launch
     static unsigned long long *d_trace = nullptr;
@@ -843,11 +943,30 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
     a.trace = d_trace;
   }
 #endif
-  if (h->fast && !replay) {
+  if (use_fast) {
     if (!do_update && !do_select) return SPGG_OK;
     fast_fn_t ff = pick_fast(h->M, h->action, do_update, do_select);
-    CUDA_TRY(launch_pdl(ff, h->g.ctas_per_rep * h->n_rep, FTHREADS, fast_smem(h->M), st, h->fmaps[h->cur], a));
+    FastMaps fm = h->fmaps[h->cur];
+    const int q_out = (do_update && h->spec) ? (h->qcur ^ 1) : h->qcur;   // ping-pong only where a re-run must be possible
+    fm.q_ld = h->qmaps[h->qcur];
+    fm.q_st = h->qmaps[q_out];
+    if (a.spec) {
+      // test hook (tests/test_gpu_speculation.py): SPGG_SPEC_TEST_POISON=n makes every n-th speculative
+      // launch guess a value that cannot be right (spec = 2), so the re-run path is exercised on demand
+      static const int poison = getenv("SPGG_SPEC_TEST_POISON") ? atoi(getenv("SPGG_SPEC_TEST_POISON")) : 0;
+      if (poison > 0 && !h->in_rerun && h->spec_launches % poison == poison - 1) a.spec = 2;
+    }
+    CUDA_TRY(launch_pdl(ff, h->g.ctas_per_rep * h->n_rep, FTHREADS, fast_smem(h->M), st, fm, a));
+    h->qcur = q_out;
+    if (do_update) {
+      h->carry_valid = h->spec;   // every fast update launch leaves its own exact maximum in gcarry
+      if (a.spec) {
+        h->spec_launches += 1;
+        if (!h->in_rerun) h->spec_iterations += 1;
+      }
+    }
   } else {
+    if (do_update) h->carry_valid = false;
     step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
     // programmatic dependent launch pays only when a launch is short (at most one tile per SM;
     // measured: 25.0 -> 23.4 us per iteration at L=100, but 366 -> 428 us for 60 batched L=200 replicas)
@@ -858,7 +977,28 @@ extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   if (do_select) h->cur ^= 1;
+  if (h->pend_rel >= 0 && h->pend_rel < (int)h->pend_cur_after.size()) {
+    h->pend_cur_after[h->pend_rel] = (char)h->cur;
+    h->pend_q_after[h->pend_rel] = (char)h->qcur;
+  }
   return SPGG_OK;
+}
+
+extern "C" int spgg_phase_kernel(spgg_t *h, int do_update, int do_select, void *stream_) {
+  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_phase_kernel outside begin/end");
+  return launch_step(h, do_update, do_select, (cudaStream_t)stream_, false);  // the caller supplies the exact maximum
+}
+
+// finish the next iteration (and choose the action of the one after it when do_select): one speculative
+// launch when the handle can guess the global maximum, else the exact pair k_gmax + k_step
+extern "C" int spgg_phase_iteration(spgg_t *h, int do_select, void *stream_) {
+  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_phase_iteration outside begin/end");
+  if (h->pend_rel >= h->pend_n) return fail(SPGG_E_STATE, "the chunk announced to spgg_begin_steps is complete");
+  int rcode = SPGG_OK;
+  if (can_speculate(h, do_select)) h->pend_rel += 1;
+  else rcode = spgg_phase_gmax(h, stream_);
+  if (!rcode) rcode = launch_step(h, 1, do_select, (cudaStream_t)stream_, true);
+  return rcode;
 }
 
 // gmax of the iteration about to be finished (pend_rel+1); advances pend_rel
@@ -904,7 +1044,7 @@ static int resident_chunk(spgg_handle *h, int n_steps, cudaStream_t st) {
   a.g = h->g;
   a.rg = h->rgeo;
   a.rc = h->d_rc;
-  a.Q = h->d_Q;
+  a.Q = h->Qcur();
   a.R = h->d_R[h->cur];
   a.S = h->d_S[h->cur];
   a.stats = h->d_stats;
@@ -982,10 +1122,7 @@ extern "C" int spgg_step(spgg_t *h, int n_steps, void *stream_) {
     return spgg_end_steps(h, stream_);
   }
   rcode = spgg_phase_kernel(h, 0, 1, stream_);  // choose the action of iteration iter+1
-  for (int s = 1; s <= n_steps && !rcode; ++s) {
-    rcode = spgg_phase_gmax(h, stream_);
-    if (!rcode) rcode = spgg_phase_kernel(h, 1, s < n_steps ? 1 : 0, stream_);
-  }
+  for (int s = 1; s <= n_steps && !rcode; ++s) rcode = spgg_phase_iteration(h, s < n_steps ? 1 : 0, stream_);
   if (rcode) return rcode;
   return spgg_end_steps(h, stream_);
 }
@@ -1013,6 +1150,8 @@ extern "C" int spgg_query(spgg_t *h, int rep, spgg_status_t *out) {
   out->n_replicas = h->n_rep;
   out->r_is_int8 = h->mode == MODE_F32_I8;
   out->kernel_launches = h->launches;
+  out->speculative_launches = h->spec_launches;
+  out->speculation_failures = h->spec_failures;
   return SPGG_OK;
 }
 
@@ -1028,10 +1167,12 @@ extern "C" int spgg_describe(spgg_t *h, char *buf, int n) {
     len = snprintf(tmp, sizeof(tmp), "resident: cluster of %d CTAs x %d threads per replica, %zu KB shared memory per CTA, "
                    "ghost rows through DSMEM (%s)", h->rgeo.CS, h->rgeo.threads, h->smem_res >> 10, arith);
   else if (h->fast)
-    len = snprintf(tmp, sizeof(tmp), "fast: TMA-staged %dx%d tiles, %d persistent CTAs per replica, two launches per iteration (%s)",
-                   FTR, TC, h->g.ctas_per_rep, arith);
+    len = snprintf(tmp, sizeof(tmp), "fast: TMA-staged %dx%d tiles, %d persistent CTAs per replica, %s (%s)",
+                   FTR, TC, h->g.ctas_per_rep,
+                   (h->spec && h->spec_on) ? "one launch per iteration (speculative global maximum, verified)"
+                                           : "two launches per iteration (k_gmax + k_step)", arith);
   else
-    len = snprintf(tmp, sizeof(tmp), "general: %dx%d tiles, %d CTAs per replica, two launches per iteration (%s)", h->g.TR, TC,
+    len = snprintf(tmp, sizeof(tmp), "general: %dx%d tiles, %d CTAs per replica, two launches per iteration (k_gmax + k_step) (%s)", h->g.TR, TC,
                    h->g.ctas_per_rep, arith);
   if (buf && n > 0) {
     strncpy(buf, tmp, (size_t)n - 1);
@@ -1049,9 +1190,9 @@ extern "C" int spgg_init_random(spgg_t *h, int rep, uint64_t seed) {
   CUDA_TRY(cudaSetDevice(h->device));
   const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
   const int grid = 148 * 8;
-  if (h->mode == MODE_F32_I8) k_init_random<ModeF32I8><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
-  else if (h->mode == MODE_F32_F) k_init_random<ModeF32F><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
-  else k_init_random<ModeF64><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
+  if (h->mode == MODE_F32_I8) k_init_random<ModeF32I8><<<grid, 256>>>(h->g, rep, h->Qcur(), h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
+  else if (h->mode == MODE_F32_F) k_init_random<ModeF32F><<<grid, 256>>>(h->g, rep, h->Qcur(), h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
+  else k_init_random<ModeF64><<<grid, 256>>>(h->g, rep, h->Qcur(), h->d_R[h->cur], h->d_S[h->cur], lo, hi, h->nq());
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   h->launches += 1;
@@ -1098,7 +1239,7 @@ extern "C" int spgg_state_digest(spgg_t *h, int rep, uint64_t out[3]) {
   CUDA_TRY(cudaMemset(d_out, 0, 3 * sizeof(unsigned long long)));
   const int grid = 148 * 8;
   const double rq = h->rc_host[rep].rq;
-#define DIGEST(Md) k_state_digest<Md><<<grid, 256>>>(h->g, rep, h->d_Q, h->d_R[h->cur], h->d_S[h->cur], h->nq(), rq, d_out)
+#define DIGEST(Md) k_state_digest<Md><<<grid, 256>>>(h->g, rep, h->Qcur(), h->d_R[h->cur], h->d_S[h->cur], h->nq(), rq, d_out)
   if (h->mode == MODE_F32_I8) DIGEST(ModeF32I8);
   else if (h->mode == MODE_F32_F) DIGEST(ModeF32F);
   else DIGEST(ModeF64);

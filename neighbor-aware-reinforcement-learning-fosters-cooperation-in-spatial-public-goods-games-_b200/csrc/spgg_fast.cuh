@@ -151,7 +151,10 @@ __device__ __forceinline__ uint32_t sh_2(uint32_t a, uint32_t b) { return __byte
 struct FastMaps {
   CUtensorMap ld_code, ld_R, ld_S;  // halo'd tile loads from the planes of iteration j
   CUtensorMap st_code, st_R, st_S;  // tile stores into the planes of iteration j+1
-  CUtensorMap q;                    // Q table as (128 B = 8 sites, L/8, rows, replicas), 128-byte swizzle
+  // Q table as (128 B = 8 sites, L/8, rows, replicas), 128-byte swizzle: read from q_ld, written to q_st
+  // (the same buffer when the handle updates Q in place, the two halves of a ping-pong pair when a
+  // failed speculation of the global maximum must be able to re-run an iteration from its inputs)
+  CUtensorMap q_ld, q_st;
 };
 
 #ifndef SPGG_FAST_MINBLOCKS
@@ -203,11 +206,14 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 
   float4 *Qp = reinterpret_cast<float4 *>(a.Q) + (long long)rep * g.site_stride;
 
-  float inv_den = 0.f;
+  float inv_den = 0.f, gm_used = 0.f;
   if (upd) {
-    const float gm = reinterpret_cast<const float *>(a.gmax)[(long long)rep * a.cap + a.rel];
-    inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));  // spgg.py:489 denominator
+    // spec: last iteration's maximum stands in for this one's until the launch has computed its own
+    gm_used = a.spec ? a.gcarry[rep] : reinterpret_cast<const float *>(a.gmax)[(long long)rep * a.cap + a.rel];
+    if (a.spec == 2) gm_used = 123.0f;   // test hook: a guess that is certainly wrong
+    inv_den = __fdiv_rn(1.0f, __fadd_rn(gm_used, rc.leps_f));  // spgg.py:489 denominator
   }
+  float gbest = 0.f;  // max over this thread's sites of the best signed neighbour difference (>= 0 kept)
   const uint32_t thr = sel ? a.thr_tab[(long long)(a.rel + 1) * g.n_rep + rep] : 0u;
   const float alpha = rc.alpha_f, gamma = rc.gamma_f, kappa = rc.kappa_f;
   // byte-parallel reputation update: steps beyond the width of [R_min, R_max] saturate alike
@@ -231,6 +237,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   const int n_tiles = g.n_tx * g.n_ty;
   // tile walk without divisions: (ty, tx) advance by (d_ty, d_tx) with a carry
   const int d_ty = g.ctas_per_rep / g.n_tx, d_tx = g.ctas_per_rep - d_ty * g.n_tx;
+  const int d_skew = (d_tx + d_ty) % g.n_tx;  // advance of the skewed column per step (one division per launch)
   auto issue = [&](int ty_, int tx_, int st) {
     const int r0 = ty_ * FTR, c0 = tx_ * TC;
     unsigned char *base = smem + st * SM::kStageBytes;
@@ -259,7 +266,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   __syncwarp();
   auto q_issue = [&](int col8, int row, int buf) {
     mbar_expect_tx(&qbar[buf], SM::kQBufBytes);
-    tma_load_4d_hint(sQ + buf * SM::kQBufBytes, &tm.q, &qbar[buf], 0, col8, row, rep, pol);
+    tma_load_4d_hint(sQ + buf * SM::kQBufBytes, &tm.q_ld, &qbar[buf], 0, col8, row, rep, pol);
   };
   // lane l owns the four consecutive sites 4l..4l+3 of a row segment: site s sits in 128-byte
   // line s>>3 at 16-byte chunk (s&7) ^ (line&7) (CU_TENSOR_MAP_SWIZZLE_128B)
@@ -274,9 +281,9 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep, ++tiles_done, stage ^= 1) {
     const int r0 = ty * FTR, c0 = tx * TC;
     // coordinates of this CTA's next tile
-    int nty = ty + d_ty, ntxs = txs + d_tx;
-    if (ntxs >= g.n_tx) { ntxs -= g.n_tx; ++nty; }
-    const int ntx = (ntxs + nty) % g.n_tx;
+    int nty = ty + d_ty, ntxs = txs + d_tx, ntx = tx + d_skew;
+    if (ntxs >= g.n_tx) { ntxs -= g.n_tx; ++nty; ++ntx; }
+    if (ntx >= g.n_tx) ntx -= g.n_tx;  // tx + d_skew + 1 < 2 n_tx, so this is (ntxs + nty) mod n_tx without a division
     const bool has_next = tile + g.ctas_per_rep < n_tiles;
     // prefetch the next tile into the other stage (its readers passed the barrier that
     // closes the previous iteration)
@@ -489,8 +496,9 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
 #pragma unroll
           for (int q = 1; q < NK; ++q) {
             const float d = __fsub_rn(nv[q], vx);
-            if (d > best) { best = d; boff = no[q]; second = (q >= 4); }
+            if (d > best) { best = d; boff = no[q]; if constexpr (M == 2) second = (q >= 4); }
           }
+          gbest = fmaxf(gbest, best);
           const bool same = ((((uint32_t)bCode[vb + k + boff] ^ code) >> 1) & 1u) == 0u;   // a* == a
           const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na[k], nb_[k]), vx), qe[k]);  // algorithms.py:128
           const float qtd = __fmaf_rn(alpha, td, qe[k]);                                   // algorithms.py:131
@@ -567,7 +575,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       fence_proxy_async();  // the updated rows become visible to the TMA engine
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d_hint(&tm.q, sQ + qb * SM::kQBufBytes, 0, c0 >> 3, r0 + warp * SM::kRowsPerWarp, rep, pol);
+        tma_store_4d_hint(&tm.q_st, sQ + qb * SM::kQBufBytes, 0, c0 >> 3, r0 + warp * SM::kRowsPerWarp, rep, pol);
         tma_store_commit();
       }
     }
@@ -652,6 +660,15 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   block_reduce_bfly<NSTAT>(v, sm_red);
   double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
   if (tid < NSTAT) part[tid] = sm_red[tid];
+  if (upd) {
+    // this launch's own global maximum: every unordered neighbour pair is seen from both ends and
+    // fsub_rn(x, y) == -fsub_rn(y, x), so max over sites of the best signed difference == max |difference|
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gbest = fmaxf(gbest, __shfl_down_sync(0xffffffffu, gbest, o));
+    // non-negative IEEE floats order like unsigned integers
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int *>(const_cast<void *>(a.gmax)) + (long long)rep * a.cap + a.rel,
+                             __float_as_uint(gbest));
+  }
   __threadfence();
   // the last tile's Q segments / tile planes were left in flight while the statistics were reduced
   if (lane == 0 && (upd || (tid == 0 && sel))) tma_store_wait_all();
@@ -683,7 +700,11 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       s[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
       s[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
       for (int z = 0; z < 4; ++z) s[ST_SUM_Q_D + z] = s[ST_SUM_Q + z] - s[ST_SUM_Q_C + z];
-      s[ST_GMAX] = (double)reinterpret_cast<const float *>(a.gmax)[(long long)rep * a.cap + a.rel];
+      // every CTA's atomicMax is ordered before its ticket: the table entry is final here
+      const float g_exact = __ldcg(reinterpret_cast<const float *>(a.gmax) + (long long)rep * a.cap + a.rel);
+      s[ST_GMAX] = (double)g_exact;
+      if (a.gcarry) a.gcarry[rep] = g_exact;
+      if (a.spec && g_exact != gm_used) atomicMin(a.bad_at, a.rel);   // the host re-runs from this launch
       for (int z = 0; z < ST_X_SN0; ++z) row[z] = s[z];
     } else {
       row[ST_SUM_R] = s[ST_SUM_R];
@@ -701,6 +722,9 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   pdl_launch_dependents();
   pdl_wait();  // the planes, the stop flags and gmax come from the kernels before this one
   const int rep = blockIdx.x / a.g.ctas_per_rep;
+  // a speculation of an EARLIER launch of this chunk failed: nothing after it may run (a failure another
+  // replica records during this very launch has the value a.rel and does not stop its siblings half way)
+  if (a.bad_at && *a.bad_at < a.rel) return;
   const int stop = a.stop_at[rep];
   if (stop >= 0 && a.j > stop) return;
   if (SEL && stop >= 0 && a.j == stop) {  // uniform lattice: finish iteration j, choose nothing (spgg.py:405)

@@ -105,6 +105,15 @@ struct KArgs {
   int rel;                 // j - (iteration at start of the spgg_step call)
   int cap;                 // rows per replica in stats/gmax tables
   int do_update, do_select;
+  // Speculative global maximum (fast path, spgg_fast.cuh).  The lattice-global max |reward difference| of
+  // iteration j (spgg.py:488) is also max over sites of the best signed neighbour difference the update
+  // computes anyway, so every update launch produces it as a by-product (atomicMax into gmax[rep][rel]).
+  // With spec != 0 the launch does not wait for a k_gmax pass: it uses the previous iteration's value
+  // (gcarry[rep]) and the last CTA compares; on a mismatch it records rel in *bad_at, every later launch of
+  // the chunk returns at once, and the host re-runs from there with the (now known) exact value.
+  int spec;                // 0 exact (gmax[rep][rel] was computed by k_gmax), 1 guess = gcarry[rep], 2 test hook: a wrong guess
+  float *gcarry;           // [n_rep] exact maximum of the last finished iteration (written by every update launch)
+  int *bad_at;             // handle-wide: INT_MAX, or the first rel whose speculation failed
 #ifdef SPGG_TRACE
   unsigned long long *trace;  // debug builds only: per CTA {start ns, end ns, smid, tiles}
 #endif

@@ -84,7 +84,7 @@ def test_resident_equals_per_iteration_kernels(monkeypatch, name, p):
         else:
             monkeypatch.delenv("SPGG_NO_RESIDENT", raising=False)
         eng = _engine(p, seeds=777, precision="fp32")
-        want = ("cooperative grid" if name.startswith("grid_") else "resident: cluster") if not no_res else "two launches"
+        want = ("cooperative grid" if name.startswith("grid_") else "resident: cluster") if not no_res else "per iteration"
         assert want in eng.describe(), eng.describe()
         eng.set_state(S0, np.zeros((L, L)), Q0)
         l0 = eng.status().kernel_launches
@@ -92,7 +92,7 @@ def test_resident_equals_per_iteration_kernels(monkeypatch, name, p):
         launches.append(eng.status().kernel_launches - l0)
         outs.append(eng.get_state() + (eng.stats(),))
         eng.close()
-    assert launches[0] == 2 and launches[1] >= 2 * n    # the resident path really ran: one launch per chunk (+ the row kernel)
+    assert launches[0] == 2 and launches[1] >= n        # the resident path really ran: one launch per chunk (+ the row kernel)
     for a, b in zip(*outs):
         if a.ndim == 2 and a.shape[1] == 40:
             assert np.array_equal(a[:, EXACT], b[:, EXACT])
