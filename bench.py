@@ -111,6 +111,19 @@ def c4_config(L, inner):
                        "transfers are amortised over the K x iterations_per_step iterations of the run"}
 
 
+def c5_config(L, world, inner):
+    """`config` of the N > 1 line (both arms print the same one)."""
+    return {"workload": f"C5: one L={L} lattice in {world} row strips, reputation state, M=1, r=3, kappa=1, "
+                        f"w_P=0.95, Q-learning; {inner} iterations per bench step, per iteration one halo "
+                        "exchange (NCCL send/recv) and one 4-float all-reduce(MAX) of the strips' reports "
+                        "(global reward-difference maximum, uniform-lattice test); statistics on, Philox draws",
+            "L": L, "iterations_per_step": inner, "n_strips": world,
+            "precision": "fp32 Q (float4) + int8 R + bit S",
+            "l2": "per-GPU state far larger than the 126 MB L2 (no flush needed)",
+            "scaling_note": "strong scaling over N>=2 at fixed L; N=1 runs config 4 (L=4096) and reports the "
+                            "one-GPU L=32768 iteration under extras.scaling_anchor"}
+
+
 def reference_root():
     """The unmodified reference: /root/reference in the build container, oracle/_ref (shipped by
     oracle/fetch_ref.py) on the GPU box, else None."""
@@ -160,7 +173,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    L_full = args.L or 4096
+    L_full = args.L or (4096 if args.gpus <= 1 else 32768)
     budget_s, rate = 150.0, 0.7e6           # ~0.6-1.2 M site-updates/s measured in the survey
     Ls = int(min(L_full, (budget_s * rate / max(1, steps + warm)) ** 0.5))
     Ls = max(128, Ls - Ls % 32)
@@ -181,7 +194,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": c4_config(L_full, args.inner),
+        "config": c4_config(L_full, args.inner) if args.gpus <= 1 else c5_config(args.L or 32768, args.gpus, args.inner),
         "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": 1, "kind": kind,
                          "sample": sample, "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0,
@@ -200,6 +213,7 @@ def main():
     ap.add_argument("--L", type=int, default=None)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extras.scaling_anchor / extras.variants")
     ap.add_argument("--cpu-L", type=int, default=4096)
     ap.add_argument("--workload", default="c4", choices=["c4", "sweep", "c1", "c2"],
                     help="c4: the headline L=4096 lattice (default); sweep: BASELINE config 3, the "
@@ -356,6 +370,12 @@ def main():
                              f"reference path ({dt:.1f} s); no copy of the reference on this box",
                    "host_cpus": os.cpu_count()}
 
+    eng.close()
+    del eng
+    extras = {}
+    if not args.no_extras:
+        extras = measure_extras(L, peak)
+
     line = {
         "metric": "site-updates/s", "value": value, "unit": "site-updates/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
@@ -368,9 +388,71 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "extras": extras,
     }
     print(json.dumps(line), flush=True)
-    eng.close()
+
+
+BYTES_PER_SITE = {"fp32": 34.25, "fp32_rfloat": 40.25, "fp64": 80.25}
+
+
+def measure_iteration(params, precision="fp32", n_warm=3, n_iter=10, seed=2024):
+    """us per iteration of one device-resident lattice (init on the device, CUDA events)."""
+    import torch
+    import spgg_b200
+    eng = spgg_b200.Engine(params, seeds=seed, precision=precision, device=0)
+    try:
+        eng.init_random(seed)
+        stream = torch.cuda.current_stream().cuda_stream
+        eng.step(n_warm, stream)
+        eng.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.step(n_iter, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        eng.sync()
+        return 1e3 * e0.elapsed_time(e1) / n_iter, eng.describe()
+    finally:
+        eng.close()
+
+
+def measure_extras(L, peak):
+    """Beside the headline: the one-GPU iteration of the L=32768 lattice the strip runs
+    split (so that N-GPU numbers can be read against the same lattice), and the paths next to the
+    headline kernel - reference precision, second-order neighbourhood, action state, a lattice side
+    that is not a multiple of 128."""
+    out = {}
+    try:
+        L5 = 32768
+        us, desc = measure_iteration(dict(C4, L=L5), n_warm=2, n_iter=6)
+        out["scaling_anchor"] = {"L": L5, "n_gpus": 1, "us_per_iteration": us,
+                                 "value": L5 * L5 / (us * 1e-6), "unit": "site-updates/s",
+                                 "roofline_frac": 34.25 * L5 * L5 / (us * 1e-6) / 1e9 / peak, "path": desc}
+    except Exception as e:
+        out["scaling_anchor"] = {"error": str(e)[:200]}
+    variants = {}
+    cases = {
+        "fp64_reference_precision": (dict(C4, L=L), "fp64", BYTES_PER_SITE["fp64"]),
+        "second_order_M2": (dict(C4, L=L, use_second_order=True), "fp32", BYTES_PER_SITE["fp32"]),
+        "action_state": (dict(C4, L=L, state_representation="action"), "fp32", BYTES_PER_SITE["fp32"]),
+        "action_state_M2": (dict(C4, L=L, state_representation="action", use_second_order=True, r=4.0,
+                                 reward_weight_payoff=1.0), "fp32", BYTES_PER_SITE["fp32"]),
+        "L4000_not_128_aligned": (dict(C4, L=4000), "fp32", BYTES_PER_SITE["fp32"]),
+        "fractional_reputation_steps_fp32_R": (dict(C4, L=L, rep_gain_C=0.3, delta_R_D=0.7), "fp32",
+                                               BYTES_PER_SITE["fp32_rfloat"]),
+    }
+    for name, (p, prec, bps) in cases.items():
+        try:
+            us, desc = measure_iteration(p, prec)
+            n = p["L"] * p["L"]
+            variants[name] = {"L": p["L"], "us_per_iteration": us, "site_updates_per_s": n / (us * 1e-6),
+                              "bytes_per_site": bps, "roofline_frac": bps * n / (us * 1e-6) / 1e9 / peak,
+                              "path": desc}
+        except Exception as e:
+            variants[name] = {"error": str(e)[:200]}
+    out["variants"] = variants
+    return out
 
 
 def bench_sweep(args):

@@ -209,6 +209,22 @@ int spgg_phase_gmax(spgg_t *h, void *cuda_stream);
  * speculative launch when the handle can guess the maximum, else k_gmax + k_step). */
 int spgg_phase_iteration(spgg_t *h, int do_select, void *cuda_stream);
 void *spgg_gmax_device_ptr(spgg_t *h);
+/* Strips and the one-launch iteration: the maximum and the uniform-lattice test
+ * (spgg.py:405,488) are lattice-global, so a strip's update launch only reports
+ * {its own maximum, holds-a-defecting-action, holds-a-cooperating-action, 0} at
+ * spgg_strip_report_ptr() (4 floats, device); the ranks max-reduce that vector and
+ * spgg_strip_verify() then compares the maximum with the guess, keeps it as the next
+ * guess and raises the stop flag.  Per iteration: [spgg_strip_iteration, or the exact
+ * pair when spgg_strip_can_speculate() says 0] -> all-reduce(MAX) of the report ->
+ * spgg_strip_verify; the halo exchange runs beside the reduce.  After the chunk:
+ * spgg_strip_failed() (same answer on every rank) and, if non-zero,
+ * spgg_strip_rewind() + the iterations from there again. */
+int spgg_strip_can_speculate(spgg_t *h, int do_select);
+int spgg_strip_iteration(spgg_t *h, int do_select, void *cuda_stream);
+void *spgg_strip_report_ptr(spgg_t *h);
+int spgg_strip_verify(spgg_t *h, void *cuda_stream);
+int spgg_strip_failed(spgg_t *h);
+int spgg_strip_rewind(spgg_t *h, int first_failed_launch);
 int spgg_begin_steps(spgg_t *h, int n_steps, void *cuda_stream);
 int spgg_end_steps(spgg_t *h, void *cuda_stream);
 

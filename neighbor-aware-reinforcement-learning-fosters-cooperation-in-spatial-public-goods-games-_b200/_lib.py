@@ -59,7 +59,8 @@ EXPORTS = (
     "spgg_halo_pack", "spgg_halo_unpack", "spgg_phase_kernel", "spgg_phase_gmax",
     "spgg_gmax_device_ptr", "spgg_begin_steps", "spgg_end_steps", "spgg_last_error",
     "spgg_abi_version", "spgg_init_random", "spgg_describe", "spgg_set_progress",
-    "spgg_state_digest", "spgg_phase_iteration",
+    "spgg_state_digest", "spgg_phase_iteration", "spgg_strip_can_speculate", "spgg_strip_iteration",
+    "spgg_strip_report_ptr", "spgg_strip_verify", "spgg_strip_failed", "spgg_strip_rewind",
 )
 
 _lib = None
@@ -94,6 +95,13 @@ def load():
     lib.spgg_phase_kernel.argtypes = [vp, i32, i32, vp]
     lib.spgg_phase_gmax.argtypes = [vp, vp]
     lib.spgg_phase_iteration.argtypes = [vp, i32, vp]
+    lib.spgg_strip_can_speculate.argtypes = [vp, i32]
+    lib.spgg_strip_iteration.argtypes = [vp, i32, vp]
+    lib.spgg_strip_report_ptr.argtypes = [vp]
+    lib.spgg_strip_report_ptr.restype = vp
+    lib.spgg_strip_verify.argtypes = [vp, vp]
+    lib.spgg_strip_failed.argtypes = [vp]
+    lib.spgg_strip_rewind.argtypes = [vp, i32]
     lib.spgg_gmax_device_ptr.argtypes = [vp]
     lib.spgg_gmax_device_ptr.restype = vp
     lib.spgg_begin_steps.argtypes = [vp, i32, vp]

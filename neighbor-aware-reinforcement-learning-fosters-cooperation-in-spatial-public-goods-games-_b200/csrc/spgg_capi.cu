@@ -68,6 +68,8 @@ struct spgg_handle {
   long long spec_launches = 0, spec_failures = 0;
   long long spec_iterations = 0;  // iterations finished by launches that guessed (re-runs not counted twice)
   bool in_rerun = false;
+  float *d_gvec = nullptr;        // strips: [cap][4] per-iteration report {max, any D, any C, -} (KArgs::gvec)
+  int last_rel = -1, last_upd = 0, last_spec = 0, last_sel = 0;  // the launch spgg_strip_verify refers to
   int pend_qcur0 = 0;
   std::vector<char> pend_cur_after, pend_q_after;  // plane / Q parity after the launch with relative index rel
   void *d_R[2] = {nullptr, nullptr};
@@ -327,7 +329,7 @@ extern "C" int spgg_abi_version(void) { return SPGG_ABI_VERSION; }
 extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
 
 static int free_all(spgg_handle *h) {
-  cudaFree(h->d_rc); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad);
+  cudaFree(h->d_rc); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad); cudaFree(h->d_gvec);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_R[i]); cudaFree(h->d_code[i]); cudaFree(h->d_S[i]); }
   cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_partials); cudaFree(h->d_tickets);
   cudaFree(h->d_stop); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_u); cudaFree(h->d_b);
@@ -576,6 +578,27 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
 // (KArgs::spec): every later launch of the chunk returned without touching anything, so the inputs of
 // the failed launch are intact (planes and Q are ping-pong pairs).  Re-run from there; the failed
 // launch left the exact maximum in gcarry, so the re-run's guess is right.
+// put the handle back where it was just before launch `bad` of the pending chunk (its inputs are intact)
+static int rewind_to_failed_launch(spgg_handle *h, int bad) {
+  h->spec_failures += 1;
+  // small lattices change their maximum every few iterations: not worth guessing there
+  if (h->spec_failures > 8 && h->spec_failures * 16 > h->spec_iterations) h->spec_on = false;
+  const int none = 0x7fffffff;
+  CUDA_TRY(cudaMemcpy(h->d_bad, &none, sizeof(int), cudaMemcpyHostToDevice));
+  // a uniform-lattice flag raised by the failed launch itself is not to be trusted
+  std::vector<int> stop(h->n_rep);
+  CUDA_TRY(cudaMemcpy(stop.data(), h->d_stop, sizeof(int) * h->n_rep, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < h->n_rep; ++r)
+    if (stop[r] == (int)(h->pend_t0 + bad) + 1) stop[r] = -1;
+  CUDA_TRY(cudaMemcpy(h->d_stop, stop.data(), sizeof(int) * h->n_rep, cudaMemcpyHostToDevice));
+  // parities as launch bad-1 left them
+  h->cur = h->pend_cur_after[bad - 1];
+  h->qcur = h->pend_q_after[bad - 1];
+  h->carry_valid = true;
+  h->pend_rel = bad - 1;
+  return SPGG_OK;
+}
+
 static int rerun_failed_speculation(spgg_handle *h) {
   for (;;) {
     int bad = 0x7fffffff;
@@ -583,22 +606,8 @@ static int rerun_failed_speculation(spgg_handle *h) {
     if (bad == 0x7fffffff) return SPGG_OK;
     if (getenv("SPGG_SPEC_DEBUG")) fprintf(stderr, "[spgg] speculation failed at launch %d of %d (t0 %lld), %lld speculative launches so far\n", bad, h->pend_n, h->pend_t0, h->spec_launches);
     if (bad < 1 || bad > h->pend_n) return fail(SPGG_E_STATE, "speculation bookkeeping out of range (%d of %d)", bad, h->pend_n);
-    h->spec_failures += 1;
-    // small lattices change their maximum every few iterations: not worth guessing there
-    if (h->spec_failures > 8 && h->spec_failures * 16 > h->spec_iterations) h->spec_on = false;
-    const int none = 0x7fffffff;
-    CUDA_TRY(cudaMemcpy(h->d_bad, &none, sizeof(int), cudaMemcpyHostToDevice));
-    // a uniform-lattice flag raised by the failed launch itself is not to be trusted
-    std::vector<int> stop(h->n_rep);
-    CUDA_TRY(cudaMemcpy(stop.data(), h->d_stop, sizeof(int) * h->n_rep, cudaMemcpyDeviceToHost));
-    for (int r = 0; r < h->n_rep; ++r)
-      if (stop[r] == (int)(h->pend_t0 + bad) + 1) stop[r] = -1;
-    CUDA_TRY(cudaMemcpy(h->d_stop, stop.data(), sizeof(int) * h->n_rep, cudaMemcpyHostToDevice));
-    // parities as launch bad-1 left them
-    h->cur = h->pend_cur_after[bad - 1];
-    h->qcur = h->pend_q_after[bad - 1];
-    h->carry_valid = true;
-    h->pend_rel = bad - 1;
+    int rcode0 = rewind_to_failed_launch(h, bad);
+    if (rcode0) return rcode0;
     h->in_rerun = true;
     const int n = h->pend_n;
     for (int s = bad; s <= n; ++s) {
@@ -624,7 +633,7 @@ static int finish_pending(spgg_handle *h) {
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->pend_stream));
   CUDA_TRY(cudaGetLastError());
-  if (h->spec && h->pend_rel == h->pend_n && !h->pend_resident) {
+  if (h->spec && h->g.wrap_rows && h->pend_rel == h->pend_n && !h->pend_resident) {  // strips: spgg_strip_failed
     int rcode = rerun_failed_speculation(h);
     if (rcode) return rcode;
   }
@@ -821,13 +830,14 @@ extern "C" int spgg_set_replay_pairs(spgg_t *h, int n_steps, int n_pairs, const 
 static int ensure_tables(spgg_handle *h, int n_steps) {
   const int need = n_steps + 1;
   if (need <= h->cap) return SPGG_OK;
-  cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_eps); cudaFree(h->d_thr);
-  h->d_gmax = nullptr; h->d_stats = nullptr; h->d_eps = nullptr; h->d_thr = nullptr;
+  cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_gvec);
+  h->d_gmax = nullptr; h->d_stats = nullptr; h->d_eps = nullptr; h->d_thr = nullptr; h->d_gvec = nullptr;
   h->cap = 0;
   CUDA_TRY(cudaMalloc(&h->d_gmax, h->elem_val() * (size_t)h->n_rep * need));
   CUDA_TRY(cudaMalloc((void **)&h->d_stats, sizeof(double) * (size_t)h->n_rep * need * NSTAT));
   CUDA_TRY(cudaMalloc((void **)&h->d_eps, sizeof(double) * (size_t)h->n_rep * (need + 1)));
   CUDA_TRY(cudaMalloc((void **)&h->d_thr, sizeof(uint32_t) * (size_t)h->n_rep * (need + 1)));
+  if (h->spec && !h->g.wrap_rows) CUDA_TRY(cudaMalloc((void **)&h->d_gvec, sizeof(float) * 4 * (size_t)need));
   h->cap = need;
   return SPGG_OK;
 }
@@ -869,11 +879,13 @@ extern "C" int spgg_begin_steps(spgg_t *h, int n_steps, void *stream_) {
   CUDA_TRY(cudaMemcpyAsync(h->d_thr, thr.data(), thr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(h->d_gmax, 0, h->elem_val() * (size_t)h->n_rep * h->cap, st));
   CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * (size_t)h->n_rep * h->cap * NSTAT, st));
+  if (h->d_gvec) CUDA_TRY(cudaMemsetAsync(h->d_gvec, 0, sizeof(float) * 4 * (size_t)h->cap, st));
   h->pending = true;
   h->pend_t0 = h->iter;
   h->pend_n = n_steps;
   h->pend_cur0 = h->cur;
   h->pend_qcur0 = h->qcur;
+  h->in_rerun = false;
   h->pend_cur_after.assign((size_t)n_steps + 1, (char)h->cur);
   h->pend_q_after.assign((size_t)n_steps + 1, (char)h->qcur);
   h->pend_rel = 0;
@@ -921,7 +933,8 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
   a.j = (int)j; a.rel = h->pend_rel; a.cap = h->cap;
   a.do_update = do_update; a.do_select = do_select;
   const bool use_fast = h->fast && !replay;
-  a.spec = 0; a.gcarry = nullptr; a.bad_at = nullptr;
+  a.spec = 0; a.gcarry = nullptr; a.bad_at = nullptr; a.gvec = nullptr;
+  if (use_fast && h->spec && !h->g.wrap_rows && h->n_rep == 1) a.gvec = h->d_gvec;
   if (use_fast && h->spec) {
     a.gcarry = h->d_gcarry;
     a.bad_at = h->d_bad;
@@ -976,6 +989,7 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
+  h->last_rel = h->pend_rel; h->last_upd = do_update; h->last_spec = a.spec; h->last_sel = do_select;
   if (do_select) h->cur ^= 1;
   if (h->pend_rel >= 0 && h->pend_rel < (int)h->pend_cur_after.size()) {
     h->pend_cur_after[h->pend_rel] = (char)h->cur;
@@ -1253,6 +1267,50 @@ extern "C" int spgg_state_digest(spgg_t *h, int rep, uint64_t out[3]) {
 }
 
 // ---------------------------------------------------------------- strips
+extern "C" int spgg_strip_can_speculate(spgg_t *h, int do_select) {
+  return (h && h->pending && h->d_gvec && h->n_rep == 1 && can_speculate(h, do_select)) ? 1 : 0;
+}
+
+extern "C" int spgg_strip_iteration(spgg_t *h, int do_select, void *stream_) {
+  if (!h || !h->pending) return fail(SPGG_E_STATE, "spgg_strip_iteration outside begin/end");
+  if (!spgg_strip_can_speculate(h, do_select)) return fail(SPGG_E_STATE, "this strip cannot guess the maximum now: run the exact pair");
+  h->pend_rel += 1;
+  return launch_step(h, 1, do_select, (cudaStream_t)stream_, true);
+}
+
+extern "C" void *spgg_strip_report_ptr(spgg_t *h) {
+  if (!h || !h->pending || !h->d_gvec || h->last_rel < 0) return nullptr;
+  return h->d_gvec + 4 * (size_t)h->last_rel;
+}
+
+extern "C" int spgg_strip_verify(spgg_t *h, void *stream_) {
+  if (!h || !h->pending || !h->d_gvec || h->last_rel < 0) return fail(SPGG_E_STATE, "spgg_strip_verify: no strip launch to verify");
+  k_strip_verify<<<1, 32, 0, (cudaStream_t)stream_>>>(h->d_gvec, h->last_rel, (int)(h->pend_t0 + h->last_rel), h->last_upd,
+                                                       h->last_spec, h->last_sel, h->d_gcarry,
+                                                       reinterpret_cast<float *>(h->d_gmax), h->d_bad, h->d_stop);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  if (h->last_upd) h->carry_valid = true;   // written by the kernel above, from the reduced report
+  return SPGG_OK;
+}
+
+// after the streams of the chunk have been synchronised: 0, or the relative index (>= 1) of the launch
+// whose guess was wrong - the same on every rank, since every rank saw the same reduced values
+extern "C" int spgg_strip_failed(spgg_t *h) {
+  if (!h || !h->d_bad) return 0;
+  int bad = 0x7fffffff;
+  if (cudaMemcpy(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(SPGG_E_CUDA, "spgg_strip_failed: copy failed");
+  return bad == 0x7fffffff ? 0 : bad;
+}
+
+// back to just before that launch: the caller re-runs iterations bad .. n of the chunk
+extern "C" int spgg_strip_rewind(spgg_t *h, int bad) {
+  if (!h || !h->pending || !h->d_bad) return fail(SPGG_E_STATE, "spgg_strip_rewind outside a chunk");
+  if (bad < 1 || bad > h->pend_n) return fail(SPGG_E_INVALID, "launch %d outside the chunk of %d", bad, h->pend_n);
+  h->in_rerun = true;   // (the test hook does not spoil re-runs; cleared by the next spgg_begin_steps)
+  return rewind_to_failed_launch(h, bad);
+}
+
 extern "C" int64_t spgg_halo_bytes(spgg_t *h) {
   if (!h) return 0;
   const Geom &g = h->g;

@@ -703,8 +703,12 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       // every CTA's atomicMax is ordered before its ticket: the table entry is final here
       const float g_exact = __ldcg(reinterpret_cast<const float *>(a.gmax) + (long long)rep * a.cap + a.rel);
       s[ST_GMAX] = (double)g_exact;
-      if (a.gcarry) a.gcarry[rep] = g_exact;
-      if (a.spec && g_exact != gm_used) atomicMin(a.bad_at, a.rel);   // the host re-runs from this launch
+      if (a.gvec) {
+        a.gvec[4 * a.rel + 0] = g_exact;            // strip: report, k_strip_verify decides (spgg_kernels.cuh)
+      } else {
+        if (a.gcarry) a.gcarry[rep] = g_exact;
+        if (a.spec && g_exact != gm_used) atomicMin(a.bad_at, a.rel);   // the host re-runs from this launch
+      }
       for (int z = 0; z < ST_X_SN0; ++z) row[z] = s[z];
     } else {
       row[ST_SUM_R] = s[ST_SUM_R];
@@ -712,6 +716,11 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     if (sel && g.wrap_rows) {  // uniform lattice after this action -> next iteration breaks (spgg.py:405)
       const double nsel = s[ST_X_NSEL];
       if (nsel == 0.0 || nsel == (double)g.site_stride) a.stop_at[rep] = a.j + 1;
+    }
+    if (a.gvec) {              // strip: does it hold a defecting / a cooperating action?
+      const double nsel = s[ST_X_NSEL];
+      a.gvec[4 * a.rel + 1] = (sel && nsel == (double)g.site_stride) ? 0.0f : 1.0f;
+      a.gvec[4 * a.rel + 2] = (sel && nsel == 0.0) ? 0.0f : 1.0f;
     }
   }
 }

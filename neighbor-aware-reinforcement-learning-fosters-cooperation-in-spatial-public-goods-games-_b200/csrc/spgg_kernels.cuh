@@ -114,6 +114,11 @@ struct KArgs {
   int spec;                // 0 exact (gmax[rep][rel] was computed by k_gmax), 1 guess = gcarry[rep], 2 test hook: a wrong guess
   float *gcarry;           // [n_rep] exact maximum of the last finished iteration (written by every update launch)
   int *bad_at;             // handle-wide: INT_MAX, or the first rel whose speculation failed
+  // Row strips (one lattice over several GPUs): the maximum and the uniform-lattice test of spgg.py:405 are
+  // lattice-global, so a strip only REPORTS - gvec[rel] = {its own maximum, 1 if it holds a defecting action,
+  // 1 if it holds a cooperating action, 0} - and k_strip_verify, run after the ranks have max-reduced that
+  // vector, does what the last CTA does for a whole lattice (compare with the guess, gcarry, stop flag)
+  float *gvec;             // [cap][4] or nullptr (whole lattice)
 #ifdef SPGG_TRACE
   unsigned long long *trace;  // debug builds only: per CTA {start ns, end ns, smid, tiles}
 #endif
@@ -1278,6 +1283,24 @@ __global__ void k_state_digest(Geom g, int rep, const void *Qd, const void *Rd, 
     atomicAdd(out + 1, dR);
     atomicAdd(out + 2, dQ);
   }
+}
+
+// Strips: the per-iteration vector {max, any D, any C, -} has been max-reduced over the ranks.  One thread.
+__global__ void k_strip_verify(float *gvec, int rel, int j, int was_upd, int was_spec, int was_sel, float *gcarry,
+                               float *gmax_tab, int *bad_at, int *stop_at) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (*bad_at < rel) return;                        // a failed guess earlier in the chunk: nothing after it ran
+  if (stop_at[0] >= 0 && j > stop_at[0]) return;    // the lattice is uniform: the launch returned at once (spgg.py:405)
+  if (was_upd) {
+    const float g_exact = gvec[4 * rel + 0];
+    const float guess = gcarry[0];
+    gmax_tab[rel] = g_exact;
+    gcarry[0] = g_exact;
+    // (was_spec == 2: the test hook made the launch use a value that is certainly not the maximum)
+    if (was_spec == 2 || (was_spec && g_exact != guess)) { atomicMin(bad_at, rel); return; }
+  }
+  // every action of the lattice is the same: the next iteration breaks (spgg.py:405)
+  if (was_sel && (gvec[4 * rel + 1] == 0.0f || gvec[4 * rel + 2] == 0.0f) && stop_at[0] < 0) stop_at[0] = j + 1;
 }
 
 }  // namespace spgg

@@ -104,7 +104,7 @@ def run_experiments(param_combinations: List[Tuple], num_processes: int = None,
         if owner != rank:
             continue
         ov = dict(overrides)
-        ov.setdefault("device", torch.cuda.current_device())
+        ov.setdefault("device", sweep.default_device())
         built = [_make_model(combos[i], ov, base_dir) for i in idx]
         records = run_models([m for m, _f in built], [f for _m, f in built])
         for i, (m, _f), rec in zip(idx, built, records):

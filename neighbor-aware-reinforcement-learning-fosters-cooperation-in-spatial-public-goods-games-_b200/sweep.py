@@ -19,6 +19,20 @@ from . import _lib as L_
 from . import series
 
 
+def default_device() -> int:
+    """The GPU of this process: under torchrun (one process per GPU) LOCAL_RANK names it - and it is
+    made torch's current device, which is 0 on every rank until somebody says otherwise; in a plain
+    process, torch's current device."""
+    import os
+    import torch
+    n = torch.cuda.device_count()
+    if "LOCAL_RANK" in os.environ and n > 0:
+        d = int(os.environ["LOCAL_RANK"]) % n
+        torch.cuda.set_device(d)
+        return d
+    return torch.cuda.current_device()
+
+
 def group_key(p: dict):
     """Replicas can share a launch iff these agree (spgg_create's batch-invariant fields)."""
     return (int(p.get("L", 50)), bool(p.get("use_second_order", True)),
@@ -112,7 +126,7 @@ def run_sweep(param_list: Sequence[dict], seeds: Sequence[int] | None = None, it
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    device = torch.cuda.current_device()
+    device = default_device()
     n = len(param_list)
     if seeds is None:
         seeds = list(range(n))

@@ -69,6 +69,8 @@ def gpu_strips(rank, world, precision, second, state, L, n_steps):
     se.step(n_steps - n_steps // 2)
     rows_b = se.stats()
     S, R, Q = se.gather_state()
+    if os.environ.get("SPGG_SPEC_TEST_POISON") and se.spec_mode:
+        assert se.reruns > 0, "the spoiled guesses were not re-run"
     se.close()
     if rank == 0:
         eng = spgg_b200.Engine(p, seeds=77, precision=precision, device=dev)
@@ -88,6 +90,51 @@ def gpu_strips(rank, world, precision, second, state, L, n_steps):
             assert np.allclose(got[:, 17], want[:, 17])
             np.testing.assert_allclose(got[1:, 4:11], want[1:, 4:11], rtol=1e-6, atol=1e-6)
             np.testing.assert_allclose(got[1:, 18:31], want[1:, 18:31], rtol=1e-4, atol=1e-3)
+    dist.barrier()
+
+
+def gpu_exit(rank, world, L):
+    """spgg.py:405 over strips: every site prefers one action, epsilon = 0 -> the lattice is uniform
+    after iteration 1 and iteration 2 breaks before acting - on every rank, although no rank sees
+    more than its strip.  Same final state and iteration count as the single handle."""
+    import torch
+    import torch.distributed as dist
+    import spgg_b200
+    from spgg_b200 import strips
+    from helpers import C1, full_params
+    dev = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    p = full_params(dict(C1, L=L, epsilon=0.0, epsilon_min=0.0))
+    rs = np.random.RandomState(8)
+    S0 = rs.randint(0, 2, (L, L))
+    R0 = np.zeros((L, L))
+    for prefer in (0, 1):                                   # all cooperate / all defect
+        Q0 = np.zeros((L, L, 2, 2))
+        Q0[..., prefer] = 1.0
+        se = strips.StripEngine(p, seed=3, precision="fp32", device=dev)
+        assert se.eng.describe().startswith("fast")
+        se.set_state_global(S0, R0, Q0)
+        se.step(6)
+        se.step(4)                                           # a chunk after the stop does nothing
+        assert se.stopped_at() == 1 and se.iteration == 1, (se.stopped_at(), se.iteration)
+        S, R, Q = se.gather_state()
+        se.close()
+        assert (S == prefer).all()
+        if rank == 0:
+            eng = spgg_b200.Engine(p, seeds=3, precision="fp32", device=dev)
+            eng.set_state(S0, R0, Q0)
+            eng.step(10)
+            st = eng.status()
+            assert st.stopped_at == 1 and st.iteration == 1
+            S1, R1, Q1 = eng.get_state()
+            eng.close()
+            assert np.array_equal(S, S1) and np.array_equal(R, R1) and np.array_equal(Q, Q1)
+    # uniform from the start: nothing runs at all
+    se = strips.StripEngine(p, seed=3, precision="fp32", device=dev)
+    se.set_state_global(np.ones((L, L), np.uint8), R0, np.zeros((L, L, 2, 2)))
+    se.step(5)
+    assert se.stopped_at() == 0 and se.iteration == 0
+    se.close()
     dist.barrier()
 
 
@@ -126,6 +173,8 @@ def main():
             host_logic(rank, world)
         elif mode == "sweep":
             gpu_sweep(rank, world)
+        elif mode == "exit":
+            gpu_exit(rank, world, int(sys.argv[3]))
         else:
             precision, second, state, L, n = sys.argv[3:8]
             gpu_strips(rank, world, precision, second == "1", state, int(L), int(n))

@@ -44,6 +44,26 @@ def test_strips_equal_single_lattice_nccl(precision, second, state, L):
         assert rc == 0, out
 
 
+def test_strips_rerun_a_wrong_guess_of_the_global_maximum():
+    """The one-launch iteration over strips with every 5th guess spoiled on purpose: the verdict comes
+    from the max-reduced report, every rank re-runs from the same launch, results unchanged."""
+    res = launch_ranks(["gpu", "gloo", "fp32", 0, "reputation", 256, 24], 2, timeout=600,
+                       extra_env={"SPGG_SPEC_TEST_POISON": "5"})
+    for rc, out in res:
+        assert rc == 0, out
+
+
+def test_strips_stop_on_a_uniform_lattice_like_the_reference():
+    """early exit (spgg.py:405) in strip mode - the uniform-lattice test is global."""
+    res = launch_ranks(["exit", "gloo", 256], 2, timeout=600)
+    for rc, out in res:
+        assert rc == 0, out
+    if _ngpu() >= 2:
+        res = launch_ranks(["exit", "nccl", 256], 2, timeout=600)
+        for rc, out in res:
+            assert rc == 0, out
+
+
 @pytest.mark.parametrize("world", [1, 2])
 def test_replica_sweep_sharded_over_ranks(world):
     """BASELINE config 3: the r x kappa grid as batched replicas dealt to the ranks; each replica
