@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip extras.scaling_anchor / extras.variants")
+    ap.add_argument("--only-variants", action="store_true", help="print extras.variants only (kernel tuning)")
     ap.add_argument("--cpu-L", type=int, default=4096)
     ap.add_argument("--workload", default="c4", choices=["c4", "sweep", "c1", "c2"],
                     help="c4: the headline L=4096 lattice (default); sweep: BASELINE config 3, the "
@@ -238,6 +239,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if args.only_variants:
+        v = measure_extras(args.L or 4096, measured_peak_gbs()[0], anchor=False)["variants"]
+        for k_, d in v.items():
+            print(f"{k_:38s} {d.get('us_per_iteration', float('nan')):9.1f} us  frac {d.get('roofline_frac', float('nan')):.3f}  {d.get('path', d.get('error', ''))[:60]}")
+        return
     if args.workload != "c4":
         return bench_sweep(args)
     dev = 0
@@ -417,13 +423,15 @@ def measure_iteration(params, precision="fp32", n_warm=3, n_iter=10, seed=2024):
         eng.close()
 
 
-def measure_extras(L, peak):
+def measure_extras(L, peak, anchor=True):
     """Beside the headline: the one-GPU iteration of the L=32768 lattice the strip runs
     split (so that N-GPU numbers can be read against the same lattice), and the paths next to the
     headline kernel - reference precision, second-order neighbourhood, action state, a lattice side
     that is not a multiple of 128."""
     out = {}
     try:
+        if not anchor:
+            raise RuntimeError("skipped")
         L5 = 32768
         us, desc = measure_iteration(dict(C4, L=L5), n_warm=2, n_iter=6)
         out["scaling_anchor"] = {"L": L5, "n_gpus": 1, "us_per_iteration": us,

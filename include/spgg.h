@@ -149,6 +149,12 @@ int spgg_set_progress(spgg_t *h, int64_t iteration, const double *epsilon);
  * compared with single-GPU runs without moving a 20 GB state through the host. */
 int spgg_state_digest(spgg_t *h, int replica, uint64_t out[3]);
 
+/* np.histogram(R, bins=n_bins, range=(edges[0], edges[n_bins])) of a replica's
+ * reputations on the device (rep_hist_* datasets, spgg.py:399-401,626-628): edges
+ * are the n_bins+1 values of np.linspace, bins are half-open except the last,
+ * the bin index is corrected against the edges as NumPy does.  n_bins <= 64. */
+int spgg_r_histogram(spgg_t *h, int replica, int n_bins, const double *edges, int64_t *counts);
+
 /* Same distributions as the reference ctor (Q ~ U(-0.01,0.01) spgg.py:121, R = 0
  * spgg.py:129, S ~ Bernoulli(1/2) spgg.py:162) generated on the device from Philox
  * keyed by `seed`; for lattices too large to stage through host memory. */

@@ -1266,6 +1266,36 @@ extern "C" int spgg_state_digest(spgg_t *h, int rep, uint64_t out[3]) {
   return SPGG_OK;
 }
 
+extern "C" int spgg_r_histogram(spgg_t *h, int rep, int n_bins, const double *edges, int64_t *counts) {
+  if (!h || !edges || !counts) return fail(SPGG_E_INVALID, "spgg_r_histogram: null argument");
+  if (rep < 0 || rep >= h->n_rep) return fail(SPGG_E_INVALID, "replica %d out of range", rep);
+  if (n_bins < 1 || n_bins > 64) return fail(SPGG_E_INVALID, "n_bins must be in [1, 64] (got %d)", n_bins);
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  double *d_edges = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_edges, sizeof(double) * 65));
+  if (cudaMalloc((void **)&d_cnt, sizeof(unsigned long long) * 64) != cudaSuccess) { cudaFree(d_edges); return fail(SPGG_E_CUDA, "cudaMalloc failed"); }
+  cudaMemcpy(d_edges, edges, sizeof(double) * (n_bins + 1), cudaMemcpyHostToDevice);
+  cudaMemset(d_cnt, 0, sizeof(unsigned long long) * 64);
+  const double rq = h->rc_host[rep].rq;
+  const int grid = 148 * 8;
+#define HIST(Md) k_r_histogram<Md><<<grid, 256>>>(h->g, rep, h->d_R[h->cur], rq, n_bins, d_edges, d_cnt)
+  if (h->mode == MODE_F32_I8) HIST(ModeF32I8);
+  else if (h->mode == MODE_F32_F) HIST(ModeF32F);
+  else HIST(ModeF64);
+#undef HIST
+  unsigned long long host_cnt[64];
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(host_cnt, d_cnt, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost);
+  cudaFree(d_edges); cudaFree(d_cnt);
+  if (e != cudaSuccess) return fail(SPGG_E_CUDA, "spgg_r_histogram: %s", cudaGetErrorString(e));
+  for (int i = 0; i < n_bins; ++i) counts[i] = (int64_t)host_cnt[i];
+  h->launches += 1;
+  return SPGG_OK;
+}
+
 // ---------------------------------------------------------------- strips
 extern "C" int spgg_strip_can_speculate(spgg_t *h, int do_select) {
   return (h && h->pending && h->d_gvec && h->n_rep == 1 && can_speculate(h, do_select)) ? 1 : 0;

@@ -561,8 +561,14 @@ __device__ __forceinline__ T sel4(int e, T a0, T a1, T a2, T a3) {
   return (e & 2) ? hi : lo;
 }
 
+// The general kernel is latency-bound (one site per thread and row, dependent shared-memory stencils):
+// what it needs is resident warps, not registers.  Measured at L=4000 (fp32, int8 R), us per iteration:
+// 1 CTA/SM (190 registers) 1604, 2 CTAs/SM 891, 3 CTAs/SM (80 registers, a few hundred bytes of spills) 718.
+#ifndef SPGG_GEN_MINBLOCKS
+#define SPGG_GEN_MINBLOCKS 3
+#endif
 template <class Md, int M, bool ACTION, bool REPLAY>
-__global__ void __launch_bounds__(MAX_THREADS) k_step(KArgs a) {
+__global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs a) {
   typedef typename Md::Q QT;
   typedef typename Md::R RT;
   typedef typename Md::Code Code;
@@ -1301,6 +1307,38 @@ __global__ void k_strip_verify(float *gvec, int rel, int j, int was_upd, int was
   }
   // every action of the lattice is the same: the next iteration breaks (spgg.py:405)
   if (was_sel && (gvec[4 * rel + 1] == 0.0f || gvec[4 * rel + 2] == 0.0f) && stop_at[0] < 0) stop_at[0] = j + 1;
+}
+
+// np.histogram(R, bins=nb, range=(edges[0], edges[nb])) of one replica's reputations (spgg.py:399-401,
+// 626-628) without moving the lattice to the host: uniform bins, the last one closed on the right, the
+// float index corrected against the edges exactly as NumPy's uniform-bin path does.  nb <= 64.
+template <class Md>
+__global__ void k_r_histogram(Geom g, int rep, const void *Rd, double rq, int nb, const double *edges,
+                              unsigned long long *counts) {
+  typedef typename Md::R RT;
+  __shared__ unsigned int s_cnt[64];
+  __shared__ double s_edge[65];
+  const RT *Rp = reinterpret_cast<const RT *>(Rd) + (long long)rep * g.plane_stride;
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0u;
+  if (threadIdx.x <= nb) s_edge[threadIdx.x] = edges[threadIdx.x];
+  __syncthreads();
+  const double lo = s_edge[0], hi = s_edge[nb];
+  const double norm = (double)nb / (hi - lo);
+  const long long n = g.site_stride;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / g.L), col = (int)(e % g.L);
+    double v = (double)Rp[(long long)(i + GH) * g.pitchB + CPAD + col];
+    if (sizeof(RT) == 1) v *= rq;
+    if (!(v >= lo && v <= hi)) continue;
+    int idx = (int)((v - lo) * norm);
+    if (idx == nb) idx -= 1;
+    if (v < s_edge[idx]) idx -= 1;
+    else if (v >= s_edge[idx + 1] && idx != nb - 1) idx += 1;
+    atomicAdd(&s_cnt[idx], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nb && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 }  // namespace spgg

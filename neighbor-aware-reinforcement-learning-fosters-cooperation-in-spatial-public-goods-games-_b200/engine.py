@@ -149,6 +149,20 @@ class Engine:
         L_.check(self.lib.spgg_state_digest(self._h, replica, out))
         return int(out[0]), int(out[1]), int(out[2])
 
+    def get_q(self, replica: int = 0):
+        """The Q table alone, as float64 in the reference's layout (the strategies and reputations stay)."""
+        n = self.rows * self.L
+        Q = np.empty(self.nq * n, np.float64)
+        L_.check(self.lib.spgg_get_state(self._h, replica, None, None, Q.ctypes.data))
+        return Q.reshape((self.rows, self.L, 2, 2) if self.nq == 4 else (self.rows, self.L, 2, 2, 2))
+
+    def r_histogram(self, bins: int, lo: float, hi: float, replica: int = 0):
+        """``np.histogram(R, bins=bins, range=(lo, hi))`` computed on the device: (counts int64, edges)."""
+        edges = np.linspace(lo, hi, bins + 1, dtype=np.float64)
+        counts = np.zeros(bins, np.int64)
+        L_.check(self.lib.spgg_r_histogram(self._h, replica, int(bins), edges.ctypes.data, counts.ctypes.data))
+        return counts, edges
+
     def set_replay(self, u, b):
         """``u`` (n,rows,L) float64 and ``b`` (n,rows,L) 0/1: the reference's draw
         arrays for the next n iterations (algorithms.py:105,108)."""

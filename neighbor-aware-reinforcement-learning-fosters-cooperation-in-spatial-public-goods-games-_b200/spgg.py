@@ -129,6 +129,12 @@ class SPGG:
         if getattr(self, "_bad_state", None) is not None:
             raise ValueError(f"Unknown state_representation: {self._bad_state}. "
                              f"Must be 'reputation' or 'action'")
+        # The reference recomputes the TD error of the neighbour-influence statistic with the ctor's alpha and
+        # gamma (spgg.py:446-473, 512) while the update itself uses the algorithm object's; the fused kernel
+        # has one pair.  An instance that disagrees with the ctor would silently change that statistic.
+        if (float(self.algorithm.alpha) != float(self.alpha) or float(self.algorithm.gamma) != float(self.gamma)):
+            raise ValueError("the RLAlgorithm instance's alpha / gamma differ from the SPGG ctor's: the reference "
+                             "mixes the two in its neighbour-influence statistic (spgg.py:446-473); pass equal values")
         if getattr(self.algorithm, "kernel_tag", None) is None:
             raise ValueError(
                 f"algorithm '{getattr(self.algorithm, 'name', type(self.algorithm).__name__)}' is not "
@@ -140,11 +146,11 @@ class SPGG:
         with ``deferred`` (a list) the histogram and the HDF5 writes are queued so the caller can
         run them while the GPU works on the next chunk."""
         S, R, _ = eng.get_state(replica, want_q=False)
+        rep_hist, rep_bins = eng.r_histogram(20, self.R_min, self.R_max, replica)   # np.histogram on the device
         snaps[i] = True
 
         def write():
             data_file.create_dataset(f"R_snapshot_{i}", data=R)
-            rep_hist, rep_bins = np.histogram(R, bins=20, range=(self.R_min, self.R_max))
             data_file.create_dataset(f"rep_hist_{i}", data=rep_hist)
             data_file.create_dataset(f"rep_bins_{i}", data=rep_bins)
             data_file.create_dataset(f"Sn_snapshot_{i}", data=S.astype(np.int64))
@@ -153,7 +159,7 @@ class SPGG:
         else:
             deferred.append(write)
 
-    def _write_final(self, data_file, ser, S, R):
+    def _write_final(self, data_file, ser, S, R, rep_hist_final, rep_bins_final):
         """Dataset names, order and dtypes of spgg.py:595-633."""
         for key in ("it_records_final", "epsilon_history_final", "rep_avg_history_final",
                     "coop_rate_history", "switch_C_to_D", "switch_D_to_C",
@@ -173,7 +179,6 @@ class SPGG:
             data_file.create_dataset(f"q_d_pos_{pos[0]}_{pos[1]}_final", data=np.zeros(0))
         data_file.create_dataset("Sn_final", data=S.astype(np.int64))
         data_file.create_dataset("R_final", data=R)
-        rep_hist_final, rep_bins_final = np.histogram(R, bins=20, range=(self.R_min, self.R_max))
         data_file.create_dataset("rep_hist_final", data=rep_hist_final)
         data_file.create_dataset("rep_bins_final", data=rep_bins_final)
         # 4-connected, non-periodic clusters of cooperators (spgg.py:631-633), linear time
@@ -306,17 +311,25 @@ def run_models(models, filenames):
         worker.join()
         launches = int(eng.status().kernel_launches)
         for r, m in enumerate(models):
-            S, R, Q = eng.get_state(r)
+            S, R, _ = eng.get_state(r, want_q=False)
+            hist_f, bins_f = eng.r_histogram(20, m.R_min, m.R_max, r)
+            ri = np.vstack(rows_it[r]) if rows_it[r] else np.zeros((0, L_.NSTAT))
+            sb = np.concatenate(sum_r_before[r]) if sum_r_before[r] else np.zeros(0)
+            # the schedule the engine ran is the algorithm object's (it may be an instance the caller built)
+            ser_params = dict(m.params, epsilon_decay=m.algorithm.epsilon_decay, epsilon_min=m.algorithm.epsilon_min)
+            ser = series.assemble(ri, sb, N, ser_params, eps0[r], stopped=stopped[r],
+                                  stop_sum_r=stop_sum_r[r] if stopped[r] else 0.0,
+                                  stop_all_coop=bool((S == 0).all()))
+            # the final datasets go to the file on the host thread while the Q table (the largest array)
+            # comes back from the device
+            worker.run([lambda m=m, r=r, ser=ser, S=S, R=R, hist_f=hist_f, bins_f=bins_f:
+                        m._write_final(files[r], ser, S, R, hist_f, bins_f)])
+            Q = eng.get_q(r)
             if eng.nq == 8:
                 m.algorithm.q_table_1 = np.ascontiguousarray(Q[:, :, 0])
                 m.algorithm.q_table_2 = np.ascontiguousarray(Q[:, :, 1])
                 Q = m.algorithm.get_combined_q_table()
-            ri = np.vstack(rows_it[r]) if rows_it[r] else np.zeros((0, L_.NSTAT))
-            sb = np.concatenate(sum_r_before[r]) if sum_r_before[r] else np.zeros(0)
-            ser = series.assemble(ri, sb, N, m.params, eps0[r], stopped=stopped[r],
-                                  stop_sum_r=stop_sum_r[r] if stopped[r] else 0.0,
-                                  stop_all_coop=bool((S == 0).all()))
-            m._write_final(files[r], ser, S, R)
+            worker.join()
             m.kernel_launches = launches
             # post-run attributes the reference leaves behind
             m.q_table, m.R, m._Sn = Q, R, S.astype(np.int64)

@@ -3,7 +3,7 @@
 # usage: bash scripts/gpu_profile.sh <tag>
 TAG=${1:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --inner 6 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 1 --inner 6 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list_${TAG}.log 2>&1
 echo "launch list rc=$?"

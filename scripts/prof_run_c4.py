@@ -17,4 +17,6 @@ m.folder = tmp
 print("ctor", round(time.perf_counter() - t0, 3), "s")
 pr = cProfile.Profile(); t0 = time.perf_counter(); pr.enable(); m.run(os.path.join(tmp, "c4.h5")); pr.disable(); dt = time.perf_counter() - t0
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(25)
-print("run", round(dt, 3), "s"); print("\n".join(l[:160] for l in s.getvalue().splitlines()[4:45]))
+print("run", round(dt, 3), "s")
+import re
+print("\n".join(re.sub(r"/\S*/", "", l)[:150] for l in s.getvalue().splitlines()[4:45]))

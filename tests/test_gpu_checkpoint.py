@@ -120,3 +120,27 @@ def test_digests_add_up_over_row_blocks():
     d1 = whole.digest()
     assert d1[0] != dw[0] and d1[1:] == dw[1:]
     whole.close()
+
+
+@pytest.mark.parametrize("precision,gain,loss", [("fp32", 1.0, 1.0), ("fp32", 0.25, 0.75), ("fp32", 0.3, 0.7),
+                                                 ("fp64", 0.3, 0.7)])
+def test_device_histogram_equals_numpy(precision, gain, loss):
+    """rep_hist_* (spgg.py:399-401,626-628): np.histogram(R, bins=20, range=(R_min, R_max)) computed on the
+    device - int8 units, fp32 and fp64 reputations, values on and between the bin edges."""
+    import spgg_b200
+    L = 96
+    p = full_params(dict(C1, L=L, rep_gain_C=gain, delta_R_D=loss))
+    rs = np.random.RandomState(1)
+    eng = spgg_b200.Engine(p, seeds=2, precision=precision)
+    eng.set_state(rs.randint(0, 2, (L, L)), np.zeros((L, L)), rs.uniform(-0.01, 0.01, (L, L, 2, 2)))
+    for n in (1, 7, 40):
+        eng.step(n)
+        _S, R, _Q = eng.get_state(want_q=False)
+        want_c, want_e = np.histogram(R, bins=20, range=(p["R_min"], p["R_max"]))
+        got_c, got_e = eng.r_histogram(20, p["R_min"], p["R_max"])
+        assert np.array_equal(got_c, want_c) and got_c.dtype == want_c.dtype
+        assert np.array_equal(got_e, want_e)
+        want_c, _ = np.histogram(R, bins=7, range=(-3.5, 2.25))      # values outside the range are dropped
+        got_c, _ = eng.r_histogram(7, -3.5, 2.25)
+        assert np.array_equal(got_c, want_c)
+    eng.close()
