@@ -225,6 +225,23 @@ void *spgg_gmax_device_ptr(spgg_t *h);
  * spgg_strip_verify; the halo exchange runs beside the reduce.  After the chunk:
  * spgg_strip_failed() (same answer on every rank) and, if non-zero,
  * spgg_strip_rewind() + the iterations from there again. */
+/* Peer-mapped halos (one process per GPU, NVLink): spgg_ipc_export() writes the
+ * cudaIpc handles of this strip's six planes (6 x 64 bytes).  A strip attaches the
+ * handles of the strip ABOVE it (the owner of row row0-1) with which = 0 and those
+ * of the strip BELOW it with which = 1; peer_rows is the number of rows that
+ * neighbour owns.  Once both sides are attached every selecting launch of the fast
+ * path stores its first / last two rows straight into the neighbours' ghost rows,
+ * and the halo pack / send / unpack between launches is not needed (the report
+ * all-reduce orders the launches of different GPUs). */
+int spgg_ipc_export(spgg_t *h, unsigned char *handles_6x64);
+int spgg_ipc_attach(spgg_t *h, int which, const unsigned char *handles_6x64, int peer_rows, int same_as_other);
+/* ... and the report itself: with spgg_ring_export / spgg_ring_attach (handles of
+ * ALL ranks, in rank order) the last CTA of a launch max-combines its report into a
+ * ring slot of every rank with system-scope atomics and counts itself in;
+ * spgg_strip_verify() then only waits (on the device) until all ranks are in.  No
+ * collective-library call between two launches of the steady state. */
+int spgg_ring_export(spgg_t *h, unsigned char *handle64);
+int spgg_ring_attach(spgg_t *h, int world, int rank, const unsigned char *handles_world_x64);
 int spgg_strip_can_speculate(spgg_t *h, int do_select);
 int spgg_strip_iteration(spgg_t *h, int do_select, void *cuda_stream);
 void *spgg_strip_report_ptr(spgg_t *h);

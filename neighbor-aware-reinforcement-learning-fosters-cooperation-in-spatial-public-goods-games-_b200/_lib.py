@@ -61,7 +61,7 @@ EXPORTS = (
     "spgg_abi_version", "spgg_init_random", "spgg_describe", "spgg_set_progress",
     "spgg_state_digest", "spgg_phase_iteration", "spgg_strip_can_speculate", "spgg_strip_iteration",
     "spgg_strip_report_ptr", "spgg_strip_verify", "spgg_strip_failed", "spgg_strip_rewind",
-    "spgg_r_histogram",
+    "spgg_r_histogram", "spgg_ipc_export", "spgg_ipc_attach", "spgg_ring_export", "spgg_ring_attach",
 )
 
 _lib = None
@@ -104,6 +104,10 @@ def load():
     lib.spgg_strip_failed.argtypes = [vp]
     lib.spgg_strip_rewind.argtypes = [vp, i32]
     lib.spgg_r_histogram.argtypes = [vp, i32, i32, vp, vp]
+    lib.spgg_ipc_export.argtypes = [vp, vp]
+    lib.spgg_ipc_attach.argtypes = [vp, i32, vp, i32, i32]
+    lib.spgg_ring_export.argtypes = [vp, vp]
+    lib.spgg_ring_attach.argtypes = [vp, i32, i32, vp]
     lib.spgg_gmax_device_ptr.argtypes = [vp]
     lib.spgg_gmax_device_ptr.restype = vp
     lib.spgg_begin_steps.argtypes = [vp, i32, vp]

@@ -69,6 +69,19 @@ struct spgg_handle {
   long long spec_iterations = 0;  // iterations finished by launches that guessed (re-runs not counted twice)
   bool in_rerun = false;
   float *d_gvec = nullptr;        // strips: [cap][4] per-iteration report {max, any D, any C, -} (KArgs::gvec)
+  // strips: planes of the strip above ([0]) / below ([1]) mapped into this process (cudaIpc), per plane parity
+  void *peer_code[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  void *peer_R[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  uint32_t *peer_S[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int peer_rows[2] = {0, 0};
+  bool peer_on = false;
+  std::vector<void *> ipc_opened;
+  // ring of report slots (KArgs::ring_peer): this strip's own, and every rank's mapped here
+  unsigned *d_ring = nullptr;
+  unsigned *ring_peer[SPGG_MAX_RING] = {nullptr};
+  int ring_world = 0;
+  int gen = 0;            // launches that pushed into the ring since the last reset (the same on every rank)
+  int last_gen = -1;
   int last_rel = -1, last_upd = 0, last_spec = 0, last_sel = 0;  // the launch spgg_strip_verify refers to
   int pend_qcur0 = 0;
   std::vector<char> pend_cur_after, pend_q_after;  // plane / Q parity after the launch with relative index rel
@@ -329,7 +342,9 @@ extern "C" int spgg_abi_version(void) { return SPGG_ABI_VERSION; }
 extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
 
 static int free_all(spgg_handle *h) {
-  cudaFree(h->d_rc); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad); cudaFree(h->d_gvec);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->ipc_opened.clear();
+  cudaFree(h->d_rc); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad); cudaFree(h->d_gvec); cudaFree(h->d_ring);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_R[i]); cudaFree(h->d_code[i]); cudaFree(h->d_S[i]); }
   cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_partials); cudaFree(h->d_tickets);
   cudaFree(h->d_stop); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_u); cudaFree(h->d_b);
@@ -721,6 +736,11 @@ static void begin_new_run(spgg_handle *h, int rep) {
   }
   h->stale[rep] = 0;
   h->carry_valid = false;  // the global maximum of the run before says nothing about this one
+  if (h->d_ring) {         // ring mode: a new run starts with empty slots (the caller synchronises the ranks)
+    cudaMemset(h->d_ring, 0, sizeof(unsigned) * RING_SLOTS * RING_WORDS);
+    h->gen = 0;
+    h->last_gen = -1;
+  }
 }
 
 extern "C" int spgg_set_state(spgg_t *h, int rep, const uint8_t *S, const double *R, const double *Q) {
@@ -934,6 +954,20 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
   a.do_update = do_update; a.do_select = do_select;
   const bool use_fast = h->fast && !replay;
   a.spec = 0; a.gcarry = nullptr; a.bad_at = nullptr; a.gvec = nullptr;
+  for (int d = 0; d < 2; ++d) {   // ghost rows of the neighbours' OUTPUT planes (parity cur^1), fast path only
+    const bool on = h->peer_on && use_fast && do_select;
+    a.peer_code[d] = on ? h->peer_code[d][h->cur ^ 1] : nullptr;
+    a.peer_R[d] = on ? h->peer_R[d][h->cur ^ 1] : nullptr;
+    a.peer_S[d] = on ? h->peer_S[d][h->cur ^ 1] : nullptr;
+    a.peer_rows[d] = h->peer_rows[d];
+  }
+  a.ring_world = 0; a.gen = 0;
+  for (int p = 0; p < SPGG_MAX_RING; ++p) a.ring_peer[p] = nullptr;
+  if (h->ring_world > 0 && use_fast && h->d_gvec && (do_update || do_select)) {
+    a.ring_world = h->ring_world;
+    a.gen = h->gen;
+    for (int p = 0; p < h->ring_world; ++p) a.ring_peer[p] = h->ring_peer[p];
+  }
   if (use_fast && h->spec && !h->g.wrap_rows && h->n_rep == 1) a.gvec = h->d_gvec;
   if (use_fast && h->spec) {
     a.gcarry = h->d_gcarry;
@@ -990,6 +1024,7 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   h->last_rel = h->pend_rel; h->last_upd = do_update; h->last_spec = a.spec; h->last_sel = do_select;
+  h->last_gen = a.ring_world > 0 ? h->gen++ : -1;
   if (do_select) h->cur ^= 1;
   if (h->pend_rel >= 0 && h->pend_rel < (int)h->pend_cur_after.size()) {
     h->pend_cur_after[h->pend_rel] = (char)h->cur;
@@ -1297,6 +1332,95 @@ extern "C" int spgg_r_histogram(spgg_t *h, int rep, int n_bins, const double *ed
 }
 
 // ---------------------------------------------------------------- strips
+// Peer-mapped planes: each strip exports the IPC handles of its six planes (code, R, S x two parities);
+// the neighbours open them and their boundary tiles store straight into this strip's ghost rows.
+extern "C" int spgg_ipc_export(spgg_t *h, unsigned char *handles /* 6 x 64 bytes */) {
+  if (!h || !handles) return fail(SPGG_E_INVALID, "spgg_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(h->device));
+  void *ptrs[6] = {h->d_code[0], h->d_code[1], h->d_R[0], h->d_R[1], h->d_S[0], h->d_S[1]};
+  for (int i = 0; i < 6; ++i) {
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, ptrs[i]));
+    memcpy(handles + 64 * i, &hd, 64);
+  }
+  return SPGG_OK;
+}
+
+// which: 0 = the strip above (row0 - 1), 1 = the strip below.  same_as_other != 0: that neighbour is the
+// one already attached on the other side (two strips), reuse its mappings instead of opening them twice.
+extern "C" int spgg_ipc_attach(spgg_t *h, int which, const unsigned char *handles, int peer_rows, int same_as_other) {
+  if (!h || (which != 0 && which != 1)) return fail(SPGG_E_INVALID, "spgg_ipc_attach: bad argument");
+  if (!h->fast || h->n_rep != 1 || h->g.wrap_rows) return fail(SPGG_E_UNSUPPORTED, "peer-mapped halos serve single-replica strips on the TMA fast path");
+  int rcode = finish_pending(h);
+  if (rcode) return rcode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  void *ptrs[6];
+  if (same_as_other) {
+    const int o = which ^ 1;
+    ptrs[0] = h->peer_code[o][0]; ptrs[1] = h->peer_code[o][1]; ptrs[2] = h->peer_R[o][0];
+    ptrs[3] = h->peer_R[o][1]; ptrs[4] = h->peer_S[o][0]; ptrs[5] = h->peer_S[o][1];
+    if (!ptrs[0]) return fail(SPGG_E_STATE, "the other neighbour is not attached yet");
+  } else {
+    if (!handles) return fail(SPGG_E_INVALID, "spgg_ipc_attach: null handles");
+    for (int i = 0; i < 6; ++i) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, handles + 64 * i, 64);
+      cudaError_t e = cudaIpcOpenMemHandle(&ptrs[i], hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(SPGG_E_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+      }
+      h->ipc_opened.push_back(ptrs[i]);
+    }
+  }
+  h->peer_code[which][0] = ptrs[0]; h->peer_code[which][1] = ptrs[1];
+  h->peer_R[which][0] = ptrs[2]; h->peer_R[which][1] = ptrs[3];
+  h->peer_S[which][0] = (uint32_t *)ptrs[4]; h->peer_S[which][1] = (uint32_t *)ptrs[5];
+  h->peer_rows[which] = peer_rows;
+  h->peer_on = h->peer_code[0][0] != nullptr && h->peer_code[1][0] != nullptr;
+  return SPGG_OK;
+}
+
+// The ring of report slots: spgg_ring_export() gives the cudaIpc handle of this strip's ring (64 bytes);
+// spgg_ring_attach() receives the handles of ALL ranks in rank order (its own entry is not opened).
+extern "C" int spgg_ring_export(spgg_t *h, unsigned char *handle64) {
+  if (!h || !handle64) return fail(SPGG_E_INVALID, "spgg_ring_export: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_ring) {
+    CUDA_TRY(cudaMalloc((void **)&h->d_ring, 2 << 20));   // its own allocation: IPC handles name whole allocations
+    CUDA_TRY(cudaMemset(h->d_ring, 0, 2 << 20));
+  }
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_ring));
+  memcpy(handle64, &hd, 64);
+  return SPGG_OK;
+}
+
+extern "C" int spgg_ring_attach(spgg_t *h, int world, int rank, const unsigned char *handles /* world x 64 */) {
+  if (!h || !handles || world < 2 || world > SPGG_MAX_RING || rank < 0 || rank >= world)
+    return fail(SPGG_E_INVALID, "spgg_ring_attach: bad argument (world %d, at most %d)", world, SPGG_MAX_RING);
+  if (!h->d_ring || !h->peer_on) return fail(SPGG_E_STATE, "spgg_ring_attach follows spgg_ring_export and the neighbours' spgg_ipc_attach");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { h->ring_peer[p] = h->d_ring; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles + 64 * p, 64);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      h->ring_world = 0;
+      return fail(SPGG_E_CUDA, "cudaIpcOpenMemHandle (ring of rank %d) failed: %s", p, cudaGetErrorString(e));
+    }
+    h->ipc_opened.push_back(ptr);
+    h->ring_peer[p] = (unsigned *)ptr;
+  }
+  h->ring_world = world;
+  h->gen = 0;
+  return SPGG_OK;
+}
+
 extern "C" int spgg_strip_can_speculate(spgg_t *h, int do_select) {
   return (h && h->pending && h->d_gvec && h->n_rep == 1 && can_speculate(h, do_select)) ? 1 : 0;
 }
@@ -1315,9 +1439,14 @@ extern "C" void *spgg_strip_report_ptr(spgg_t *h) {
 
 extern "C" int spgg_strip_verify(spgg_t *h, void *stream_) {
   if (!h || !h->pending || !h->d_gvec || h->last_rel < 0) return fail(SPGG_E_STATE, "spgg_strip_verify: no strip launch to verify");
-  k_strip_verify<<<1, 32, 0, (cudaStream_t)stream_>>>(h->d_gvec, h->last_rel, (int)(h->pend_t0 + h->last_rel), h->last_upd,
-                                                       h->last_spec, h->last_sel, h->d_gcarry,
-                                                       reinterpret_cast<float *>(h->d_gmax), h->d_bad, h->d_stop);
+  if (h->last_gen >= 0)   // ring mode: the ranks combined their reports themselves; wait for all of them, then the verdict
+    k_ring_verify<<<1, 32, 0, (cudaStream_t)stream_>>>(h->d_ring, h->last_gen, h->ring_world, h->d_gvec, h->last_rel,
+                                                      (int)(h->pend_t0 + h->last_rel), h->last_upd, h->last_spec, h->last_sel,
+                                                      h->d_gcarry, reinterpret_cast<float *>(h->d_gmax), h->d_bad, h->d_stop);
+  else
+    k_strip_verify<<<1, 32, 0, (cudaStream_t)stream_>>>(h->d_gvec, h->last_rel, (int)(h->pend_t0 + h->last_rel), h->last_upd,
+                                                         h->last_spec, h->last_sel, h->d_gcarry,
+                                                         reinterpret_cast<float *>(h->d_gmax), h->d_bad, h->d_stop);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   if (h->last_upd) h->carry_valid = true;   // written by the kernel above, from the reduced report
@@ -1338,6 +1467,11 @@ extern "C" int spgg_strip_rewind(spgg_t *h, int bad) {
   if (!h || !h->pending || !h->d_bad) return fail(SPGG_E_STATE, "spgg_strip_rewind outside a chunk");
   if (bad < 1 || bad > h->pend_n) return fail(SPGG_E_INVALID, "launch %d outside the chunk of %d", bad, h->pend_n);
   h->in_rerun = true;   // (the test hook does not spoil re-runs; cleared by the next spgg_begin_steps)
+  if (h->d_ring) {      // ring mode: every rank empties its own ring and starts counting launches again; the
+    CUDA_TRY(cudaMemset(h->d_ring, 0, sizeof(unsigned) * RING_SLOTS * RING_WORDS));  // caller puts a barrier
+    h->gen = 0;                                                                        // between this and the re-run
+    h->last_gen = -1;
+  }
   return rewind_to_failed_launch(h, bad);
 }
 

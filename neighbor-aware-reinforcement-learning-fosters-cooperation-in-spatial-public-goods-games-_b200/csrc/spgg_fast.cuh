@@ -592,7 +592,9 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       // cells that have copies are visited (store_cell writes the cell and all its copies)
       const bool ecol0 = tx == 0, ecol1 = tx == g.n_tx - 1;
       const bool erow0 = g.wrap_rows && ty == 0, erow1 = g.wrap_rows && ty == g.n_ty - 1;
-      const bool edge = ecol0 || ecol1 || erow0 || erow1;
+      // strips: the rows a neighbour GPU needs go straight into its ghost rows (peer-mapped planes)
+      const bool prow0 = a.peer_code[0] != nullptr && ty == 0, prow1 = a.peer_code[1] != nullptr && ty == g.n_ty - 1;
+      const bool edge = ecol0 || ecol1 || erow0 || erow1 || prow0 || prow1;
       if (edge) {
         uint8_t *code_out = reinterpret_cast<uint8_t *>(a.code_out) + (long long)rep * g.plane_stride;
         int8_t *R_out = reinterpret_cast<int8_t *>(a.R_out) + (long long)rep * g.plane_stride;
@@ -600,27 +602,41 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         // items 0..2*FTR*GC-1: the GC first / last columns; then 2*GH*TC: the GH first / last rows
         for (int e = tid; e < 2 * FTR * GC + 2 * GH * TC; e += FTHREADS) {
           int rr, cc;
-          bool on;
+          bool on, peer = false;
+          int side = 0;
           if (e < 2 * FTR * GC) {
-            const int side = e >= FTR * GC, q = side ? e - FTR * GC : e;
+            side = e >= FTR * GC;
+            const int q = side ? e - FTR * GC : e;
             rr = q / GC;
             cc = side ? TC - GC + (q % GC) : q % GC;
             on = side ? ecol1 : ecol0;
           } else {
-            const int q0 = e - 2 * FTR * GC, side = q0 >= GH * TC, q = side ? q0 - GH * TC : q0;
+            const int q0 = e - 2 * FTR * GC;
+            side = q0 >= GH * TC;
+            const int q = side ? q0 - GH * TC : q0;
             rr = side ? FTR - GH + q / TC : q / TC;
             cc = q % TC;
             on = side ? erow1 : erow0;
+            peer = side ? prow1 : prow0;
           }
+          const int o = rr * TC + cc;
           if (on) {
-            const int o = rr * TC + cc;
             store_cell<uint8_t>(code_out, g, r0 + rr, c0 + cc, out_code[o]);
             store_cell<int8_t>(R_out, g, r0 + rr, c0 + cc, out_R[o]);
+          }
+          if (peer) {
+            // row index in the neighbour's frame: my first rows are its rows peer_rows .. peer_rows+GH-1
+            // (bottom ghosts), my last GH rows its rows -GH .. -1 (top ghosts); store_cell adds the column images
+            const int pi = side ? (rr - FTR) : (a.peer_rows[0] + rr);
+            store_cell<uint8_t>(reinterpret_cast<uint8_t *>(a.peer_code[side]), g, pi, c0 + cc, out_code[o]);
+            store_cell<int8_t>(reinterpret_cast<int8_t *>(a.peer_R[side]), g, pi, c0 + cc, out_R[o]);
           }
         }
         for (int e = tid; e < FTR * 4; e += FTHREADS) {
           const int rr = e >> 2, wi = (c0 >> 5) + (e & 3);
-          store_bits_word(S_out, g, r0 + rr, wi, out_S[e]);
+          if (ecol0 || ecol1 || erow0 || erow1) store_bits_word(S_out, g, r0 + rr, wi, out_S[e]);
+          if (prow0 && rr < GH) store_bits_word(a.peer_S[0], g, a.peer_rows[0] + rr, wi, out_S[e]);
+          if (prow1 && rr >= FTR - GH) store_bits_word(a.peer_S[1], g, rr - FTR, wi, out_S[e]);
         }
         __syncthreads();  // out_* is read above; the next tile overwrites it
       }
@@ -660,6 +676,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   block_reduce_bfly<NSTAT>(v, sm_red);
   double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
   if (tid < NSTAT) part[tid] = sm_red[tid];
+  if (a.peer_code[0] != nullptr || a.peer_code[1] != nullptr) __threadfence_system();  // rows stored into a neighbour's planes
   if (upd) {
     // this launch's own global maximum: every unordered neighbour pair is seen from both ends and
     // fsub_rn(x, y) == -fsub_rn(y, x), so max over sites of the best signed difference == max |difference|
@@ -719,8 +736,26 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     }
     if (a.gvec) {              // strip: does it hold a defecting / a cooperating action?
       const double nsel = s[ST_X_NSEL];
-      a.gvec[4 * a.rel + 1] = (sel && nsel == (double)g.site_stride) ? 0.0f : 1.0f;
-      a.gvec[4 * a.rel + 2] = (sel && nsel == 0.0) ? 0.0f : 1.0f;
+      const float anyD = (sel && nsel == (double)g.site_stride) ? 0.0f : 1.0f;
+      const float anyC = (sel && nsel == 0.0) ? 0.0f : 1.0f;
+      a.gvec[4 * a.rel + 1] = anyD;
+      a.gvec[4 * a.rel + 2] = anyC;
+      if (a.ring_world > 0) {
+        // ring mode: combine the report into slot (gen & 3) of every rank, then count this rank in.  The
+        // halo rows this launch stored into the neighbours' planes were fenced by their CTAs before they
+        // took their tickets, and this thread saw every ticket: arrival implies the rows are there.
+        const unsigned mbits = upd ? __float_as_uint(a.gvec[4 * a.rel + 0]) : 0u;
+        const int so = (a.gen & (RING_SLOTS - 1)) * RING_WORDS;
+        __threadfence_system();
+        for (int p = 0; p < a.ring_world; ++p) {
+          unsigned *slot = a.ring_peer[p] + so;
+          atomicMax_system(slot + 0, mbits);
+          if (anyD != 0.0f) atomicMax_system(slot + 1, 1u);
+          if (anyC != 0.0f) atomicMax_system(slot + 2, 1u);
+        }
+        __threadfence_system();
+        for (int p = 0; p < a.ring_world; ++p) atomicAdd_system(a.ring_peer[p] + so + 3, 1u);
+      }
     }
   }
 }

@@ -78,6 +78,11 @@ struct Geom {
   long long site_stride;  // sites per replica, rows*L
 };
 
+#ifndef SPGG_MAX_RING
+#define SPGG_MAX_RING 16
+#endif
+constexpr int RING_SLOTS = 4, RING_WORDS = 4;   // per slot: max bits, any D, any C, arrivals
+
 struct KArgs {
   Geom g;
   const RepConst *rc;
@@ -119,6 +124,19 @@ struct KArgs {
   // 1 if it holds a cooperating action, 0} - and k_strip_verify, run after the ranks have max-reduced that
   // vector, does what the last CTA does for a whole lattice (compare with the guess, gcarry, stop flag)
   float *gvec;             // [cap][4] or nullptr (whole lattice)
+  // Strips with peer-mapped planes (cudaIpc, NVLink): the boundary tiles store their first / last GH rows
+  // straight into the ghost rows of the strip above ([0]) / below ([1]) - the OUTPUT planes of this launch
+  // on that GPU - so no halo message is packed, sent and unpacked between two launches.  nullptr: no peer.
+  void *peer_code[2];
+  void *peer_R[2];
+  uint32_t *peer_S[2];
+  int peer_rows[2];        // rows the neighbour owns (its bottom ghost rows start at that row index)
+  // ... and a 4-slot ring of {max bits, any D, any C, arrivals} per strip, mapped by every rank: the last CTA
+  // of a launch max-combines its report into slot (gen & 3) of EVERY rank and then counts itself in; the
+  // one-thread kernel k_ring_verify of each rank waits until all ranks are in and takes the verdict.  No
+  // collective library call between two launches.  ring_world == 0: no ring (NCCL all-reduce of gvec).
+  unsigned *ring_peer[SPGG_MAX_RING];
+  int ring_world, gen;
 #ifdef SPGG_TRACE
   unsigned long long *trace;  // debug builds only: per CTA {start ns, end ns, smid, tiles}
 #endif
@@ -1296,7 +1314,9 @@ __global__ void k_strip_verify(float *gvec, int rel, int j, int was_upd, int was
                                float *gmax_tab, int *bad_at, int *stop_at) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (*bad_at < rel) return;                        // a failed guess earlier in the chunk: nothing after it ran
-  if (stop_at[0] >= 0 && j > stop_at[0]) return;    // the lattice is uniform: the launch returned at once (spgg.py:405)
+  // the lattice is uniform (spgg.py:405): the launch returned at once - or, at the stopping iteration itself,
+  // only finished the update and had nothing to do if it was a select-only launch
+  if (stop_at[0] >= 0 && (j > stop_at[0] || (j == stop_at[0] && !was_upd))) return;
   if (was_upd) {
     const float g_exact = gvec[4 * rel + 0];
     const float guess = gcarry[0];
@@ -1339,6 +1359,38 @@ __global__ void k_r_histogram(Geom g, int rep, const void *Rd, double rq, int nb
   }
   __syncthreads();
   if (threadIdx.x < nb && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// Strips, ring mode: wait until every rank has combined its report of launch `gen` into this rank's ring slot,
+// publish it as gvec[rel] and take the verdict (k_strip_verify's logic).  One thread; spins on its own memory.
+__global__ void k_ring_verify(unsigned *ring, int gen, int world, float *gvec, int rel, int j, int was_upd, int was_spec,
+                              int was_sel, float *gcarry, float *gmax_tab, int *bad_at, int *stop_at) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (*bad_at < rel) return;                        // nothing after a failed guess ran - and nothing was pushed
+  // uniform lattice: the launch returned at once on every rank (or was a select-only launch at the stop)
+  if (stop_at[0] >= 0 && (j > stop_at[0] || (j == stop_at[0] && !was_upd))) return;
+  volatile unsigned *slot = ring + (gen & (RING_SLOTS - 1)) * RING_WORDS;
+  const long long t0 = clock64();
+  while (slot[3] < (unsigned)world) {
+    if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a rank is missing - fail loudly instead of hanging
+    __nanosleep(200);
+  }
+  __threadfence_system();
+  const float g_exact = __uint_as_float(slot[0]);
+  const float anyD = slot[1] ? 1.0f : 0.0f, anyC = slot[2] ? 1.0f : 0.0f;
+  gvec[4 * rel + 0] = g_exact; gvec[4 * rel + 1] = anyD; gvec[4 * rel + 2] = anyC;
+  // slot gen+2 (= gen-2) was consumed two launches ago and no rank can push into it before it has seen this
+  // rank's arrival for gen+1, which is enqueued after this kernel
+  unsigned *nxt = ring + ((gen + 2) & (RING_SLOTS - 1)) * RING_WORDS;
+  nxt[0] = 0u; nxt[1] = 0u; nxt[2] = 0u; nxt[3] = 0u;
+  __threadfence_system();
+  if (was_upd) {
+    const float guess = gcarry[0];
+    gmax_tab[rel] = g_exact;
+    gcarry[0] = g_exact;
+    if (was_spec == 2 || (was_spec && g_exact != guess)) { atomicMin(bad_at, rel); return; }
+  }
+  if (was_sel && (anyD == 0.0f || anyC == 0.0f) && stop_at[0] < 0) stop_at[0] = j + 1;
 }
 
 }  // namespace spgg

@@ -146,6 +146,12 @@ class StripEngine:
         if self.world > 1 and not self.host_staged:
             ranks = dist.get_process_group_ranks(group) if group is not None else list(range(self.world))
             self.group2 = dist.new_group(ranks=ranks)
+        # peer-mapped halos: with NCCL (one GPU per rank, NVLink) the neighbours map each other's planes and
+        # the boundary tiles store their rows straight into the neighbour's ghost rows
+        self.p2p = False
+        self.ring = False
+        if self.world > 1 and not self.host_staged and os.environ.get("SPGG_NO_P2P_HALO") is None:
+            self.p2p = self._attach_neighbours()
         self.iteration = 0
         self._last_n = 0
         self._open = 0          # iterations of the chunk still to be settled (0: none)
@@ -153,6 +159,46 @@ class StripEngine:
         self.spec_mode = False
         self.reruns = 0
         self._uniform_start = False
+
+    def _attach_neighbours(self) -> bool:
+        """Exchange the IPC handles of the planes with the two neighbours (all ranks take part).  False -
+        on every rank - if any rank could not map its neighbours: the NCCL halo exchange stays."""
+        dist, lib, h = self.dist, self.lib, self.h
+        mine = (C.c_ubyte * 384)()
+        ok = lib.spgg_ipc_export(h, mine) == 0
+        everyone: list = [None] * self.world
+        dist.all_gather_object(everyone, (bytes(mine) if ok else None, self.rows), group=self.group)
+        up, down = neighbours(self.world, self.rank)
+        if ok and all(e[0] is not None for e in everyone):
+            for which, peer in ((0, up), (1, down)):
+                same = 1 if (which == 1 and down == up) else 0
+                buf = (C.c_ubyte * 384).from_buffer_copy(everyone[peer][0])
+                if lib.spgg_ipc_attach(h, which, buf, int(everyone[peer][1]), same) != 0:
+                    ok = False
+                    break
+        else:
+            ok = False
+        flags: list = [None] * self.world
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        if not all(flags):
+            return False
+        # the ring of report slots: every rank maps every rank's
+        self.ring = False
+        if os.environ.get("SPGG_NO_RING") is None and self.world <= 16:
+            one = (C.c_ubyte * 64)()
+            ok = lib.spgg_ring_export(h, one) == 0
+            rings: list = [None] * self.world
+            dist.all_gather_object(rings, bytes(one) if ok else None, group=self.group)
+            if all(r is not None for r in rings):
+                allh = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(rings))
+                ok = lib.spgg_ring_attach(h, self.world, self.rank, allh) == 0
+            else:
+                ok = False
+            dist.all_gather_object(flags, bool(ok), group=self.group)
+            self.ring = all(flags)
+            if not self.ring and ok:
+                raise RuntimeError("some rank could not map the report rings; set SPGG_NO_RING=1")
+        return True
 
     # -- state
     def set_state_global(self, S, R, Q):
@@ -182,6 +228,8 @@ class StripEngine:
         self.eng.init_random(seed)
         self.iteration = 0
         self._uniform_start = False
+        if self.ring:
+            self.dist.barrier(group=self.group)   # a new run empties the rings: nobody pushes before all did
 
     def get_state_local(self, want_q=True):
         self._settle()
@@ -245,6 +293,12 @@ class StripEngine:
         ptr = self.lib.spgg_strip_report_ptr(self.h)
         rep = torch.as_tensor(_DevArray(ptr, 4, "<f4"), device=self.dev)
         main = torch.cuda.current_stream()
+        if self.ring:
+            # the ranks combined their reports themselves (system-scope atomics into every rank's ring);
+            # one thread waits on the device until all are in and takes the verdict
+            L_.check(self.lib.spgg_strip_verify(self.h, self._stream()))
+            self._side_ev = None
+            return
         if self.world == 1 or self.host_staged:
             self._reduce_max(rep, self.group)
             L_.check(self.lib.spgg_strip_verify(self.h, self._stream()))
@@ -269,9 +323,12 @@ class StripEngine:
         lib, h = self.lib, self.h
         st = self._stream()
         sel = 1 if s < n else 0
-        self._exchange(st)                                   # codes / R / strategies just written
+        if not (self.p2p and self.spec_mode):
+            self._exchange(st)                               # codes / R / strategies just written
         if self.spec_mode:
-            self._join_side()                                # the verdict on the previous launch
+            # the verdict on the previous launch; with peer-mapped halos this reduce is also what orders
+            # the neighbours' stores into my ghost rows before my next launch reads them
+            self._join_side()
             if lib.spgg_strip_can_speculate(h, sel):
                 L_.check(lib.spgg_strip_iteration(h, sel, st))
             else:                                            # no guess yet: the exact pair
@@ -321,6 +378,8 @@ class StripEngine:
                 break
             self.reruns += 1
             L_.check(self.lib.spgg_strip_rewind(self.h, bad))
+            if self.ring:
+                self.dist.barrier(group=self.group)   # every ring is empty before anyone pushes again
             for s in range(bad, n + 1):
                 self._iteration(s, n, self._gtab)
         self._open = 0
