@@ -239,7 +239,10 @@ int spgg_ipc_attach(spgg_t *h, int which, const unsigned char *handles_6x64, int
  * ALL ranks, in rank order) the last CTA of a launch max-combines its report into a
  * ring slot of every rank with system-scope atomics and counts itself in;
  * spgg_strip_verify() then only waits (on the device) until all ranks are in.  No
- * collective-library call between two launches of the steady state. */
+ * collective-library call between two launches of the steady state.  A state
+ * upload (spgg_set_state / spgg_init_random) and spgg_strip_rewind empty the ring:
+ * the caller synchronises the ranks (a barrier) between that and the next launch,
+ * and before destroying a handle whose planes and ring the neighbours still map. */
 int spgg_ring_export(spgg_t *h, unsigned char *handle64);
 int spgg_ring_attach(spgg_t *h, int world, int rank, const unsigned char *handles_world_x64);
 int spgg_strip_can_speculate(spgg_t *h, int do_select);

@@ -412,6 +412,9 @@ class StripEngine:
     def close(self):
         try:
             self._settle()
+            if self.p2p:   # the neighbours store into this strip's planes and ring: free them only when all are done
+                self.torch.cuda.synchronize(self.dev)
+                self.dist.barrier(group=self.group)
         finally:
             self.eng.close()
 
@@ -497,6 +500,7 @@ def bench_main(args, rank: int, local_rank: int, world: int):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     L_.check(se.lib.spgg_set_state(se.h, 0, S_h.data_ptr(), R_h.data_ptr(), Q_h.data_ptr()))
+    dist.barrier()      # a new run empties the report rings: nobody steps before every rank has uploaded
     d2h = 0
     for _ in range(K):
         se.step(inner)

@@ -51,6 +51,11 @@ def test_strips_rerun_a_wrong_guess_of_the_global_maximum():
                        extra_env={"SPGG_SPEC_TEST_POISON": "5"})
     for rc, out in res:
         assert rc == 0, out
+    if _ngpu() >= 2:     # peer-mapped halos + report ring: the re-run empties the rings behind a barrier
+        res = launch_ranks(["gpu", "nccl", "fp32", 0, "reputation", 512, 24], 2, timeout=600,
+                           extra_env={"SPGG_SPEC_TEST_POISON": "5"})
+        for rc, out in res:
+            assert rc == 0, out
 
 
 def test_strips_stop_on_a_uniform_lattice_like_the_reference():
