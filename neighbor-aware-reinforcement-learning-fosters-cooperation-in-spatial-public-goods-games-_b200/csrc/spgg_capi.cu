@@ -244,14 +244,19 @@ static cudaError_t launch_pdl(void (*kern)(KArgsT...), int grid, int block, size
 
 // ---------------------------------------------------------------- fast path plumbing
 typedef void (*fast_fn_t)(const FastMaps, KArgs);
-template <int M, bool ACTION>
-static fast_fn_t pick_fast2(int upd, int sel) {
-  if (upd) return sel ? k_step_fast<M, ACTION, true, true> : k_step_fast<M, ACTION, true, false>;
-  return k_step_fast<M, ACTION, false, true>;
+template <int M, bool ACTION, bool PART>
+static fast_fn_t pick_fast3(int upd, int sel) {
+  if (upd) return sel ? k_step_fast<M, ACTION, true, true, PART> : k_step_fast<M, ACTION, true, false, PART>;
+  return k_step_fast<M, ACTION, false, true, PART>;
 }
-static fast_fn_t pick_fast(int M, int action, int upd, int sel) {
-  if (M == 2) return action ? pick_fast2<2, true>(upd, sel) : pick_fast2<2, false>(upd, sel);
-  return action ? pick_fast2<1, true>(upd, sel) : pick_fast2<1, false>(upd, sel);
+template <int M, bool ACTION>
+static fast_fn_t pick_fast2(int upd, int sel, bool part) {
+  return part ? pick_fast3<M, ACTION, true>(upd, sel) : pick_fast3<M, ACTION, false>(upd, sel);
+}
+// part: the lattice side is a multiple of 32 but not of 128 (partial last tile column)
+static fast_fn_t pick_fast(int M, int action, int upd, int sel, bool part) {
+  if (M == 2) return action ? pick_fast2<2, true>(upd, sel, part) : pick_fast2<2, false>(upd, sel, part);
+  return action ? pick_fast2<1, true>(upd, sel, part) : pick_fast2<1, false>(upd, sel, part);
 }
 static size_t fast_smem(int M) { return M == 2 ? FastSmem<2>::kTotal : FastSmem<1>::kTotal; }
 typedef void (*gfast_fn_t)(const CUtensorMap, GArgs);
@@ -294,7 +299,7 @@ static ResGeom resident_geom(int L, int cs, size_t smem_limit, int grid = 0) {
 }
 
 static int make_map(CUtensorMap *map, void *base, uint64_t row_bytes, uint64_t n_rows, uint64_t n_rep,
-                    uint64_t rep_stride_bytes, uint32_t box_bytes, uint32_t box_rows) {
+                    uint64_t rep_stride_bytes, uint32_t box_bytes, uint32_t box_rows, uint64_t visible_bytes = 0) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -303,7 +308,8 @@ static int make_map(CUtensorMap *map, void *base, uint64_t row_bytes, uint64_t n
     if (!fn || q != cudaDriverEntryPointSuccess) return fail(SPGG_E_CUDA, "cuTensorMapEncodeTiled not available");
     encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   }
-  const cuuint64_t dims[3] = {row_bytes, n_rows, n_rep};
+  // visible_bytes < row_bytes: the tensor ends before the pitch (loads beyond it give zeros, stores are dropped)
+  const cuuint64_t dims[3] = {visible_bytes ? visible_bytes : row_bytes, n_rows, n_rep};
   const cuuint64_t strides[2] = {row_bytes, rep_stride_bytes};
   const cuuint32_t box[3] = {box_bytes, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -415,7 +421,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   // fast path (spgg_fast.cuh): int8 throughput mode on 128-aligned lattices, |R| <= 15 units
   {
     const RepConst &r0 = h->rc_host[0];
-    bool ok = (h->mode == MODE_F32_I8) && (g.L % TC == 0) && (g.rows % FTR == 0) &&
+    bool ok = (h->mode == MODE_F32_I8) && (g.L % 32 == 0) && (g.L >= TC) && (g.rows % FTR == 0) &&
               p0.algorithm == SPGG_ALGO_QLEARNING && getenv("SPGG_NO_FAST") == nullptr;
     for (int r = 0; r < n_replicas && ok; ++r)
       ok = h->rc_host[r].rmin_i >= -15 && h->rc_host[r].rmax_i <= 15 && h->rc_host[r].gain_i >= 0 &&
@@ -509,10 +515,10 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   }
   if (h->fast) {
     for (int v = 0; v < 3; ++v) {
-      fast_fn_t fv = pick_fast(h->M, h->action, v != 2, v != 1);
+      fast_fn_t fv = pick_fast(h->M, h->action, v != 2, v != 1, g.L % TC != 0);
       CUDA_TRY(cudaFuncSetAttribute(fv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem(h->M)));
     }
-    fast_fn_t ff = pick_fast(h->M, h->action, 1, 1);
+    fast_fn_t ff = pick_fast(h->M, h->action, 1, 1, g.L % TC != 0);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff, FTHREADS, fast_smem(h->M)));
     CUDA_TRY(cudaFuncSetAttribute(pick_gfast(h->M), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gfast_smem(h->M)));
     int gocc = 1;
@@ -564,8 +570,10 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
       int e = make_map(&fm.ld_code, h->d_code[i], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, FROWB, rowsCR);
       if (!e) e = make_map(&fm.ld_R, h->d_R[i], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, FROWB, rowsCR);
       if (!e) e = make_map(&fm.ld_S, h->d_S[i], (uint64_t)g.pitchW * 4, nrows, n_replicas, (uint64_t)g.bits_stride * 4, FSROWB, rowsS);
-      if (!e) e = make_map(&fm.st_code, h->d_code[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
-      if (!e) e = make_map(&fm.st_R, h->d_R[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR);
+      // the store maps end at the last column of the lattice: a partial last tile writes nothing beyond it
+      // (ghost columns and padding are the edge path's business)
+      if (!e) e = make_map(&fm.st_code, h->d_code[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR, (uint64_t)(CPAD + g.L));
+      if (!e) e = make_map(&fm.st_R, h->d_R[i ^ 1], (uint64_t)g.pitchB, nrows, n_replicas, (uint64_t)g.plane_stride, TC, FTR, (uint64_t)(CPAD + g.L));
       if (!e) e = make_map(&fm.st_S, h->d_S[i ^ 1], (uint64_t)g.pitchW * 4, nrows, n_replicas, (uint64_t)g.bits_stride * 4, TC / 8, FTR);
       if (!e) e = make_map_q(&h->qmaps[i], h->d_Qb[(i == 1 && h->spec) ? 1 : 0], (uint64_t)g.L, (uint64_t)g.rows, (uint64_t)n_replicas);
       if (e) { free_all(h); delete h; return e; }
@@ -992,7 +1000,7 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
 #endif
   if (use_fast) {
     if (!do_update && !do_select) return SPGG_OK;
-    fast_fn_t ff = pick_fast(h->M, h->action, do_update, do_select);
+    fast_fn_t ff = pick_fast(h->M, h->action, do_update, do_select, h->g.L % TC != 0);
     FastMaps fm = h->fmaps[h->cur];
     const int q_out = (do_update && h->spec) ? (h->qcur ^ 1) : h->qcur;   // ping-pong only where a re-run must be possible
     fm.q_ld = h->qmaps[h->qcur];

@@ -162,7 +162,12 @@ struct FastMaps {
 #endif
 // UPD / SEL are compile-time so the four sites a thread handles per row form one straight-line
 // block the scheduler can interleave.
-template <int M, bool ACTION, bool UPD, bool SEL>
+// PART: the lattice side is a multiple of 32 but not of 128 - the last tile column is partial.  Its tiles
+// are loaded and computed like any other (the bytes right of the ghost columns are zero, TMA zero-fills
+// beyond a row, and the store maps end at column L so nothing lands outside the lattice); the lanes whose
+// four sites lie beyond L ("phantom" lanes, whole 32-bit words because L is a multiple of 4) are kept out
+// of every statistic and of the global maximum.
+template <int M, bool ACTION, bool UPD, bool SEL, bool PART = false>
 __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &a) {
   typedef FastSmem<M> SM;
   constexpr int NK = (M == 2) ? 12 : 4;
@@ -292,6 +297,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       if (sel) tma_store_wait_read();  // the previous tile's stores have left out_*
     }
     mbar_wait(&bars[stage], (uint32_t)(tiles_done >> 1) & 1u);  // a stage completes once every 2 tiles
+    const bool lv = !PART || (c0 + 4 * lane < g.L);            // this lane's four sites exist
+    const uint32_t vm = lv ? 0x01010101u : 0u;
     const unsigned char *st_base = smem + stage * SM::kStageBytes;
     const uint32_t *st_code = reinterpret_cast<const uint32_t *>(st_base + SM::kStageCode);
     const uint32_t *st_R = reinterpret_cast<const uint32_t *>(st_base + SM::kStageR);
@@ -340,7 +347,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
     if (upd) {
       // defectors per 5-site group (spgg.py:586-592), bit-sliced: one thread = 32 sites
       const int t2 = tid - 64;
-      if (t2 >= 0 && t2 < FTR * 4) {
+      if (t2 >= 0 && t2 < FTR * 4 && (!PART || (c0 >> 5) + (t2 & 3) < ((g.L + 31) >> 5))) {
         const int row = (t2 >> 2) + 2, bw = (t2 & 3) + 4;
         const uint32_t *bp = st_S + row * (FSROWB / 4) + bw;
         const uint32_t c = bp[0], u = bp[-(FSROWB / 4)], d = bp[FSROWB / 4];
@@ -407,7 +414,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           StW = flo | (fhi << 8);
         }
       }
-      sum_r = __dp4a((int)RW, 0x01010101, sum_r);          // spgg.py:394
+      sum_r = __dp4a((int)RW, (int)vm, sum_r);              // spgg.py:394
       uint32_t codeW = 0;
       float vc[4], vu[4], vd[4], vl[2], vr[2], vu2[4], vd2[4], vul = 0.f, vur = 0.f, vdl = 0.f, vdr = 0.f;
       const int vb = (rr + M) * FROWB + CPAD + 4 * lane;  // float / byte index of (rr, 4*lane) in the staged planes
@@ -415,7 +422,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         codeW = st_code[wo + M * FROWW];
         {  // integer statistics of iteration j: class = C_old*2 + coop (spgg.py:383,419-420), 4 sites per dp4a
           const uint32_t Cb = (codeW >> 2) & 0x01010101u, Ab = (codeW >> 1) & 0x01010101u;
-          const uint32_t m3 = Cb & Ab, m2 = Cb ^ m3, m1 = Ab ^ m3, m0 = 0x01010101u ^ (Cb | Ab);
+          const uint32_t m3 = Cb & Ab & vm, m2 = (Cb & vm) ^ m3, m1 = (Ab & vm) ^ m3, m0 = vm & ~(Cb | Ab);
           const uint32_t sn = (codeW >> 3) & 0x1F1F1F1Fu;
           cls_n[0] = __dp4a(m0, 0x01010101u, cls_n[0]); cls_sn[0] = __dp4a(sn, m0, cls_sn[0]);
           cls_n[1] = __dp4a(m1, 0x01010101u, cls_n[1]); cls_sn[1] = __dp4a(sn, m1, cls_sn[1]);
@@ -498,7 +505,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
             const float d = __fsub_rn(nv[q], vx);
             if (d > best) { best = d; boff = no[q]; if constexpr (M == 2) second = (q >= 4); }
           }
-          gbest = fmaxf(gbest, best);
+          if (lv) gbest = fmaxf(gbest, best);
           const bool same = ((((uint32_t)bCode[vb + k + boff] ^ code) >> 1) & 1u) == 0u;   // a* == a
           const float td = __fsub_rn(__fmaf_rn(gamma, fmaxf(na[k], nb_[k]), vx), qe[k]);  // algorithms.py:128
           const float qtd = __fmaf_rn(alpha, td, qe[k]);                                   // algorithms.py:131
@@ -510,9 +517,11 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
           const float td2 = __fsub_rn(__fmaf_rn(gamma, fmaxf(na2, nb2), vx), qtd);
           qfin[k] = __fadd_rn(qtd, nu);                                                    // spgg.py:509
           const float an = fabsf(nu);
-          s_ni += __fdividef(an, fabsf(alpha * td2) + an + 1e-8f);               // x100 at the fold; spgg.py:512
-          if (has_ratio) s_ratio += sm_ratio[code >> 1];  // zero for defecting codes
-          if (best > 0.f) pk_best += second ? 0x10001u : 1u;
+          if (lv) {
+            s_ni += __fdividef(an, fabsf(alpha * td2) + an + 1e-8f);             // x100 at the fold; spgg.py:512
+            if (has_ratio) s_ratio += sm_ratio[code >> 1];  // zero for defecting codes
+            if (best > 0.f) pk_best += second ? 0x10001u : 1u;
+          }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<float *>(qbuf + qoff[k] + eidx[k]) = qfin[k];
@@ -520,8 +529,10 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         for (int k = 0; k < 4; ++k) {
           const float4 qn = *reinterpret_cast<const float4 *>(qbuf + qoff[k]);   // after both updates
           const float m = ((codeW >> (8 * k + 2)) & 1u) ? 1.0f : 0.0f;           // was a cooperator
-          sq0 += qn.x; sq1 += qn.y; sq2 += qn.z; sq3 += qn.w;                    // spgg.py:562-583
-          sc0 = fmaf(m, qn.x, sc0); sc1 = fmaf(m, qn.y, sc1); sc2 = fmaf(m, qn.z, sc2); sc3 = fmaf(m, qn.w, sc3);
+          if (lv) {
+            sq0 += qn.x; sq1 += qn.y; sq2 += qn.z; sq3 += qn.w;                  // spgg.py:562-583
+            sc0 = fmaf(m, qn.x, sc0); sc1 = fmaf(m, qn.y, sc1); sc2 = fmaf(m, qn.z, sc2); sc3 = fmaf(m, qn.w, sc3);
+          }
         }
       }
       if (sel) {
@@ -560,7 +571,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         reinterpret_cast<uint32_t *>(out_code)[oo] = (SNW << 3) | (CW << 2) | (coopW << 1) | StW;
         reinterpret_cast<uint32_t *>(out_R)[oo] = rnewW;
         // strategy bits: this lane's 4 coop flags -> nibble; 8 lanes -> one 32-site word (bit = 1: defect)
-        const uint32_t nib = ((coopW * 0x01020408u) >> 24) & 0xFu;
+        const uint32_t nib = lv ? (((coopW * 0x01020408u) >> 24) & 0xFu) : 0u;   // phantom lanes count as defecting bits nobody stores
         uint32_t coopbits = nib << ((lane & 7) * 4);
         coopbits |= __shfl_xor_sync(0xffffffffu, coopbits, 1);
         coopbits |= __shfl_xor_sync(0xffffffffu, coopbits, 2);
@@ -585,7 +596,9 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
       if (tid == 0) {
         tma_store_3d(&tm.st_code, out_code, CPAD + c0, r0 + GH, rep);
         tma_store_3d(&tm.st_R, out_R, CPAD + c0, r0 + GH, rep);
-        tma_store_3d(&tm.st_S, out_S, (WPAD * 4) + (c0 >> 3), r0 + GH, rep);
+        // a partial last tile stores its strategy words with the edge path below (it is an edge tile anyway):
+        // the 16-byte box would have to be cut inside a 16-byte unit, which is not something to ask of TMA
+        if (!PART || c0 + TC <= g.L) tma_store_3d(&tm.st_S, out_S, (WPAD * 4) + (c0 >> 3), r0 + GH, rep);
         tma_store_commit();
       }
       // periodic copies other tiles read: ghost columns / ghost rows, edge tiles only; just the
@@ -608,7 +621,8 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
             side = e >= FTR * GC;
             const int q = side ? e - FTR * GC : e;
             rr = q / GC;
-            cc = side ? TC - GC + (q % GC) : q % GC;
+            const int wl = PART ? min(TC, g.L - c0) : TC;        // columns of this tile that exist
+            cc = side ? wl - GC + (q % GC) : q % GC;
             on = side ? ecol1 : ecol0;
           } else {
             const int q0 = e - 2 * FTR * GC;
@@ -616,8 +630,9 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
             const int q = side ? q0 - GH * TC : q0;
             rr = side ? FTR - GH + q / TC : q / TC;
             cc = q % TC;
-            on = side ? erow1 : erow0;
-            peer = side ? prow1 : prow0;
+            const bool exists = !PART || c0 + cc < g.L;          // partial last tile column: columns beyond the lattice
+            on = exists && (side ? erow1 : erow0);
+            peer = exists && (side ? prow1 : prow0);
           }
           const int o = rr * TC + cc;
           if (on) {
@@ -634,6 +649,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
         }
         for (int e = tid; e < FTR * 4; e += FTHREADS) {
           const int rr = e >> 2, wi = (c0 >> 5) + (e & 3);
+          if (PART && wi >= ((g.L + 31) >> 5)) continue;       // words beyond the lattice
           if (ecol0 || ecol1 || erow0 || erow1) store_bits_word(S_out, g, r0 + rr, wi, out_S[e]);
           if (prow0 && rr < GH) store_bits_word(a.peer_S[0], g, a.peer_rows[0] + rr, wi, out_S[e]);
           if (prow1 && rr >= FTR - GH) store_bits_word(a.peer_S[1], g, rr - FTR, wi, out_S[e]);
@@ -760,7 +776,7 @@ __device__ __forceinline__ void step_fast_body(const FastMaps &tm, const KArgs &
   }
 }
 
-template <int M, bool ACTION, bool UPD, bool SEL>
+template <int M, bool ACTION, bool UPD, bool SEL, bool PART = false>
 __global__ void __launch_bounds__(FTHREADS, SPGG_FAST_MINBLOCKS)
 k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   pdl_launch_dependents();
@@ -772,10 +788,10 @@ k_step_fast(const __grid_constant__ FastMaps tm, KArgs a) {
   const int stop = a.stop_at[rep];
   if (stop >= 0 && a.j > stop) return;
   if (SEL && stop >= 0 && a.j == stop) {  // uniform lattice: finish iteration j, choose nothing (spgg.py:405)
-    if constexpr (UPD) step_fast_body<M, ACTION, true, false>(tm, a);
+    if constexpr (UPD) step_fast_body<M, ACTION, true, false, PART>(tm, a);
     return;
   }
-  step_fast_body<M, ACTION, UPD, SEL>(tm, a);
+  step_fast_body<M, ACTION, UPD, SEL, PART>(tm, a);
 }
 
 // lattice-global max |reward difference| of iteration j (spgg.py:486-488), fast path.
@@ -846,6 +862,7 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
     if (lane == 0 && tile + n_gw < n_tiles) issue(tile + n_gw, stage ^ 1);
     mbar_wait(&bars[stage], (uint32_t)(done >> 1) & 1u);
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(stg + stage * SM::kStageBytes) + (CPAD / 4);
+    const bool lv = (tile % g.n_tx) * TC + 4 * lane < g.L;   // partial last tile column: lanes beyond the lattice
     float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f};  // rewards one / two rows up
     float u1l = 0.f, u1r = 0.f;                                        // ... and their row-neighbours
 #pragma unroll 3
@@ -868,7 +885,7 @@ k_gmax_fast(const __grid_constant__ CUtensorMap ld_code, GArgs a) {
         const float hr1 = tl[((wr >> 1) & 0x7Fu) << 5];
         if (lane == 31) r1 = hr1;
       }
-      if (s >= M) {  // a row of the tile: pairs with the rows above and to the left
+      if (s >= M && lv) {  // a row of the tile: pairs with the rows above and to the left
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           upd(k, u1[k], c[k]);                                   // (1,0)

@@ -114,6 +114,11 @@ F32_CASES = [
     ("fast_act_m2_L256", dict(C2, L=256)),
     ("fast_rep_m2_L640", dict(C1, L=640, use_second_order=True)),
     ("fast_halfR_L128", dict(C1, L=128, rep_gain_C=0.5, R_min=-7, R_max=7.5)),
+    # sides that are multiples of 32 but not of 128: the last tile column is partial (round 2)
+    ("fast_part_rep_m1_L160", dict(C1, L=160)),
+    ("fast_part_act_m2_L224", dict(C2, L=224)),
+    ("fast_part_rep_m2_L416", dict(C1, L=416, use_second_order=True, r=3.6)),
+    ("fast_part_act_m1_L288", dict(C2, L=288, use_second_order=False, r=3.0, reward_weight_payoff=0.9)),
 ]
 
 
@@ -130,6 +135,8 @@ def test_fp32_philox_vs_oracle_bit_exact(monkeypatch, name, p):
     Q0 = rs.uniform(-0.01, 0.01, (L, L, 2, 2)).astype(np.float32).astype(np.float64)
     S0 = rs.randint(0, 2, (L, L))
     eng = _engine(p, seeds=4242, precision="fp32")
+    if name.startswith("fast_"):
+        assert eng.describe().startswith("fast"), eng.describe()
     eng.set_state(S0, np.zeros((L, L)), Q0)
     eng.step(n)
     S, R, Q = eng.get_state()
@@ -147,11 +154,13 @@ def test_fp32_philox_vs_oracle_bit_exact(monkeypatch, name, p):
     eng.close()
 
 
+@pytest.mark.parametrize("L", [256, 352])
 @pytest.mark.parametrize("second", [False, True])
 @pytest.mark.parametrize("state", ["reputation", "action"])
-def test_fast_path_equals_general_path(monkeypatch, second, state):
-    """The TMA/SWAR kernel and the general kernel are two layouts of the same arithmetic."""
-    L, n = 256, 25
+def test_fast_path_equals_general_path(monkeypatch, second, state, L):
+    """The TMA/SWAR kernel and the general kernel are two layouts of the same arithmetic (L=352: with a
+    partial last tile column)."""
+    n = 25
     p = full_params(dict(C1, L=L, use_second_order=second, state_representation=state))
     rs = np.random.RandomState(21)
     Q0 = rs.uniform(-0.01, 0.01, (L, L, 2, 2))

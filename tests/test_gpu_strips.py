@@ -19,6 +19,7 @@ def _ngpu():
     ("fp32", 1, "action", 256, 4),
     ("fp32", 1, "reputation", 100, 3),      # general path, ragged strips
     ("fp64", 0, "reputation", 64, 2),
+    ("fp32", 0, "reputation", 160, 2),      # fast path with a partial last tile column, 80-row strips
     # the benchmarked tile geometry: n_tx = 32 tile columns, 2048-row strips, every persistent CTA
     # walks several tiles and the strip's own top / bottom tiles take the ghost-row path
     ("fp32", 0, "reputation", 4096, 2),
