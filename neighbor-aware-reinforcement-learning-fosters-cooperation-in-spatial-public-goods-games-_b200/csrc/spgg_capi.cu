@@ -4,6 +4,7 @@
 #include "../../include/spgg.h"
 #include "spgg_kernels.cuh"
 #include "spgg_fast.cuh"
+#include "spgg_lean.cuh"
 #include "spgg_resident.cuh"
 
 #include <cudaTypedefs.h>
@@ -55,6 +56,10 @@ struct spgg_handle {
   size_t smem_step = 0, smem_gmax = 0;
   // device memory
   RepConst *d_rc = nullptr;
+  double *d_valtab = nullptr;  // fp64 mode: {reward, ratio} per reward code and replica (k_build_valtab)
+  bool lean = false;           // Q-learning on the general path: update launches run k_step_lean
+  bool lean_gmax = false;      // general path: k_gmax_lean instead of k_gmax
+  int gmax_ctas_gen = 1;       // CTAs per replica of the general path's k_gmax launch
   void *d_Qb[2] = {nullptr, nullptr};  // [1] only with spec: Q is then read from [qcur] and written to [qcur^1]
   int qcur = 0;
   void *Qcur() const { return d_Qb[qcur]; }
@@ -208,7 +213,31 @@ static step_fn_t pick_step(int mode, int M, int action, int replay) {
     default: return pick_step1<ModeF64>(M, action, replay);
   }
 }
-static gmax_fn_t pick_gmax(int mode, int M) {
+template <class Md, int M>
+static step_fn_t pick_lean2(int action, int replay) {
+  if (action) return replay ? k_step_lean<Md, M, true, true> : k_step_lean<Md, M, true, false>;
+  return replay ? k_step_lean<Md, M, false, true> : k_step_lean<Md, M, false, false>;
+}
+template <class Md>
+static step_fn_t pick_lean1(int M, int action, int replay) {
+  return M == 2 ? pick_lean2<Md, 2>(action, replay) : pick_lean2<Md, 1>(action, replay);
+}
+// the lean Q-learning update of the general path (spgg_lean.cuh)
+static step_fn_t pick_lean(int mode, int M, int action, int replay) {
+  switch (mode) {
+    case MODE_F32_I8: return pick_lean1<ModeF32I8>(M, action, replay);
+    case MODE_F32_F: return pick_lean1<ModeF32F>(M, action, replay);
+    default: return pick_lean1<ModeF64>(M, action, replay);
+  }
+}
+static gmax_fn_t pick_gmax(int mode, int M, bool lean) {
+  if (lean) {   // k_gmax_lean: same value, every pair once
+    switch (mode) {
+      case MODE_F32_I8: return M == 2 ? k_gmax_lean<ModeF32I8, 2> : k_gmax_lean<ModeF32I8, 1>;
+      case MODE_F32_F: return M == 2 ? k_gmax_lean<ModeF32F, 2> : k_gmax_lean<ModeF32F, 1>;
+      default: return M == 2 ? k_gmax_lean<ModeF64, 2> : k_gmax_lean<ModeF64, 1>;
+    }
+  }
   switch (mode) {
     case MODE_F32_I8: return M == 2 ? k_gmax<ModeF32I8, 2> : k_gmax<ModeF32I8, 1>;
     case MODE_F32_F: return M == 2 ? k_gmax<ModeF32F, 2> : k_gmax<ModeF32F, 1>;
@@ -350,7 +379,7 @@ extern "C" const char *spgg_last_error(void) { return g_err.c_str(); }
 static int free_all(spgg_handle *h) {
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   h->ipc_opened.clear();
-  cudaFree(h->d_rc); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad); cudaFree(h->d_gvec); cudaFree(h->d_ring);
+  cudaFree(h->d_rc); cudaFree(h->d_valtab); cudaFree(h->d_Qb[0]); cudaFree(h->d_Qb[1]); cudaFree(h->d_gcarry); cudaFree(h->d_bad); cudaFree(h->d_gvec); cudaFree(h->d_ring);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_R[i]); cudaFree(h->d_code[i]); cudaFree(h->d_S[i]); }
   cudaFree(h->d_gmax); cudaFree(h->d_stats); cudaFree(h->d_partials); cudaFree(h->d_tickets);
   cudaFree(h->d_stop); cudaFree(h->d_eps); cudaFree(h->d_thr); cudaFree(h->d_u); cudaFree(h->d_b);
@@ -507,11 +536,20 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   int occ = 1;
+  h->lean = !h->fast && p0.algorithm == 0 && getenv("SPGG_NO_LEAN") == nullptr;
+  h->lean_gmax = getenv("SPGG_NO_LEAN") == nullptr;
   for (int replay = 0; replay < 2; ++replay) {
     step_fn_t f = pick_step(h->mode, h->M, h->action, replay);
     CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
     if (!replay)
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, h->threads, h->smem_step));
+    if (h->lean) {
+      // the persistent grid is sized for the kernel that runs every iteration
+      step_fn_t fl = pick_lean(h->mode, h->M, h->action, replay);
+      CUDA_TRY(cudaFuncSetAttribute(fl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
+      if (!replay)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fl, h->threads, h->smem_step));
+    }
   }
   if (h->fast) {
     for (int v = 0; v < 3; ++v) {
@@ -527,12 +565,17 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     h->gmax_ctas = (int)std::max<long long>(1, std::min<long long>((n_tiles_g + GWARPS - 1) / GWARPS,
                        ((long long)prop.multiProcessorCount * std::max(1, gocc)) / n_replicas));
   }
-  CUDA_TRY(cudaFuncSetAttribute(pick_gmax(h->mode, h->M), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(pick_gmax(h->mode, h->M, h->lean_gmax), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)h->smem_gmax));
   if (occ < 1) { delete h; return fail(SPGG_E_CUDA, "kernel does not fit on an SM (smem %zu)", h->smem_step); }
   const long long n_tiles = (long long)g.n_tx * g.n_ty;
   long long per_rep = std::max<long long>(1, ((long long)prop.multiProcessorCount * occ) / n_replicas);
   g.ctas_per_rep = (int)std::min<long long>(n_tiles, per_rep);
+  {
+    int gocc = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, pick_gmax(h->mode, h->M, h->lean_gmax), h->threads, h->smem_gmax));
+    h->gmax_ctas_gen = (int)std::min<long long>(n_tiles, std::max<long long>(1, ((long long)prop.multiProcessorCount * std::max(1, gocc)) / n_replicas));
+  }
   // the fast kernel's packed 16-bit counters bound the sites one thread may visit per launch
   if (h->fast && (g.site_stride / ((long long)g.ctas_per_rep * FTHREADS)) > 60000) h->fast = false;
   h->spec = h->fast && getenv("SPGG_NO_SPEC") == nullptr;
@@ -580,6 +623,15 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
     }
   }
   CUDA_TRY(cudaMemcpy(h->d_rc, h->rc_host.data(), sizeof(RepConst) * n_replicas, cudaMemcpyHostToDevice));
+  if (h->mode == MODE_F64) {
+    const size_t vb = sizeof(double) * 2 * ((size_t)n_replicas << VALTAB_BITS);
+    if (cudaMalloc((void **)&h->d_valtab, vb) != cudaSuccess) {
+      free_all(h); delete h;
+      return fail(SPGG_E_CUDA, "cudaMalloc(%zu bytes) failed (reward table)", vb);
+    }
+    k_build_valtab<<<dim3((1u << VALTAB_BITS) / 256, (unsigned)n_replicas), 256>>>(h->d_rc, h->d_valtab);
+    CUDA_TRY(cudaGetLastError());
+  }
   std::vector<int> neg(n_replicas, -1);
   CUDA_TRY(cudaMemcpy(h->d_stop, neg.data(), sizeof(int) * n_replicas, cudaMemcpyHostToDevice));
   if (h->spec) {
@@ -685,7 +737,9 @@ static int finish_pending(spgg_handle *h) {
     if (h->n_rep > 1) {
       for (int r = 0; r < h->n_rep; ++r) {
         if (stop[r] >= 0 && stop[r] < t_end) {
-          const int src = h->pend_cur0 ^ (int)((stop[r] - h->pend_t0) & 1);
+          // k < 0: the replica stopped in an earlier chunk and no launch of this one touched it
+          const long long k = (long long)stop[r] - h->pend_t0;
+          const int src = k >= 0 ? (h->pend_cur0 ^ (int)(k & 1)) : h->pend_cur0;
           if (src != h->cur) {
             const Geom &g = h->g;
             CUDA_TRY(cudaMemcpy((char *)h->d_R[h->cur] + (size_t)r * g.plane_stride * h->elem_R(),
@@ -695,7 +749,7 @@ static int finish_pending(spgg_handle *h) {
                                 h->d_S[src] + (size_t)r * g.bits_stride,
                                 (size_t)g.bits_stride * 4, cudaMemcpyDeviceToDevice));
           }
-          const int qsrc = h->pend_q_after[(size_t)(stop[r] - h->pend_t0)];
+          const int qsrc = k >= 0 ? h->pend_q_after[(size_t)k] : h->pend_qcur0;
           if (qsrc != h->qcur) {   // ping-pong Q: the stopped replica's table stayed in the other buffer
             const size_t qb = (size_t)h->g.site_stride * h->nq() * h->elem_Q();
             CUDA_TRY(cudaMemcpy((char *)h->d_Qb[h->qcur] + (size_t)r * qb, (char *)h->d_Qb[qsrc] + (size_t)r * qb, qb,
@@ -945,6 +999,7 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
   a.code_in = h->d_code[h->cur]; a.code_out = h->d_code[h->cur ^ 1];
   a.S_in = h->d_S[h->cur]; a.S_out = h->d_S[h->cur ^ 1];
   a.gmax = h->d_gmax; a.stats = h->d_stats; a.partials = h->d_partials;
+  a.valtab = h->d_valtab;
   a.tickets = h->d_tickets; a.stop_at = h->d_stop;
   a.eps_tab = h->d_eps; a.thr_tab = h->d_thr;
   const size_t np_ = (size_t)h->replay_pairs, ss = (size_t)h->g.site_stride;
@@ -1022,7 +1077,8 @@ static int launch_step(spgg_handle *h, int do_update, int do_select, cudaStream_
     }
   } else {
     if (do_update) h->carry_valid = false;
-    step_fn_t f = pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
+    step_fn_t f = (h->lean && do_update) ? pick_lean(h->mode, h->M, h->action, replay ? 1 : 0)
+                                          : pick_step(h->mode, h->M, h->action, replay ? 1 : 0);
     // programmatic dependent launch pays only when a launch is short (at most one tile per SM;
     // measured: 25.0 -> 23.4 us per iteration at L=100, but 366 -> 428 us for 60 batched L=200 replicas)
     const int grid = h->g.ctas_per_rep * h->n_rep;
@@ -1068,14 +1124,16 @@ extern "C" int spgg_phase_gmax(spgg_t *h, void *stream_) {
   a.rc = h->d_rc;
   a.code_in = h->d_code[h->cur];
   a.gmax = h->d_gmax;
+  a.valtab = h->d_valtab;
   a.stop_at = h->d_stop;
   a.j = (int)(h->pend_t0 + h->pend_rel); a.rel = h->pend_rel; a.cap = h->cap;
   if (h->fast) {
     CUDA_TRY(launch_pdl(pick_gfast(h->M), h->gmax_ctas * h->n_rep, GWARPS * 32, gfast_smem(h->M), st,
                         h->fmaps[h->cur].ld_code, a));
   } else {
-    gmax_fn_t f = pick_gmax(h->mode, h->M);
-    const int grid = h->g.ctas_per_rep * h->n_rep;
+    gmax_fn_t f = pick_gmax(h->mode, h->M, h->lean_gmax);
+    a.g.ctas_per_rep = h->gmax_ctas_gen;   // a light kernel: its own persistent grid (more CTAs per SM than k_step)
+    const int grid = h->gmax_ctas_gen * h->n_rep;
     if ((long long)h->g.n_tx * h->g.n_ty * h->n_rep <= 160) CUDA_TRY(launch_pdl(f, grid, h->threads, h->smem_gmax, st, a));
     else f<<<grid, h->threads, h->smem_gmax, st>>>(a);
   }
@@ -1229,8 +1287,8 @@ extern "C" int spgg_describe(spgg_t *h, char *buf, int n) {
                    (h->spec && h->spec_on) ? "one launch per iteration (speculative global maximum, verified)"
                                            : "two launches per iteration (k_gmax + k_step)", arith);
   else
-    len = snprintf(tmp, sizeof(tmp), "general: %dx%d tiles, %d CTAs per replica, two launches per iteration (k_gmax + k_step) (%s)", h->g.TR, TC,
-                   h->g.ctas_per_rep, arith);
+    len = snprintf(tmp, sizeof(tmp), "general: %dx%d tiles, %d CTAs per replica, two launches per iteration (k_gmax + %s) (%s)", h->g.TR, TC,
+                   h->g.ctas_per_rep, h->lean ? "k_step_lean" : "k_step", arith);
   if (buf && n > 0) {
     strncpy(buf, tmp, (size_t)n - 1);
     buf[n - 1] = 0;

@@ -94,6 +94,10 @@ struct KArgs {
   const uint32_t *S_in;
   uint32_t *S_out;
   const void *gmax;        // Val[n_rep][cap]
+  // fp64 mode: {reward, reward-ratio statistic} of every reward code, [n_rep][1 << 17][2], indexed by code >> 1
+  // (k_build_valtab: the same operations in the same order as payoff_f64 / reward_f64, so a lookup is the
+  // bit-identical value without the fp64 division per staged site); nullptr: compute
+  const double *valtab;
   double *stats;           // [n_rep][cap][NSTAT]
   double *partials;        // [n_rep][ctas_per_rep][NSTAT]
   unsigned *tickets;       // [n_rep]
@@ -238,10 +242,20 @@ __device__ __forceinline__ double reward_f64(uint32_t code, double P, const RepC
   return __dadd_rn(__dmul_rn(rc.wP, P), __dmul_rn(rc.wR, rr));
 }
 
+constexpr int VALTAB_BITS = 17;   // code >> 1: coop, C_old and the five 3-bit group counts
+
+// sum of the five 3-bit group counts of an fp64-mode code (bits 3..17): SigmaN of the fp32 modes
+__device__ __forceinline__ uint32_t sigma_n_of_code(uint32_t code) {
+  const uint32_t x = code >> 3;
+  const uint32_t a = x & 070707u, b = (x >> 3) & 0707u;          // digits 0,2,4 / 1,3 spaced 6 bits apart
+  return (((a * 010101u) >> 12) & 63u) + (((b * 0101u) >> 6) & 63u);
+}
+
 template <class Md>
 __device__ __forceinline__ typename Md::Val val_of_code(typename Md::Code code, const RepConst &rc,
-                                                        const float *sm_tab) {
+                                                        const float *sm_tab, const double *valtab = nullptr) {
   if constexpr (Md::kFp64) {
+    if (valtab) return __ldg(valtab + 2 * (size_t)(code >> 1));
     return reward_f64(code, payoff_f64(code, rc), rc);
   } else {
     return sm_tab[code >> 1];
@@ -465,6 +479,7 @@ struct GArgs {
   const RepConst *rc;
   const void *code_in;
   void *gmax;          // Val[n_rep][cap], zeroed at the start of the spgg_step call
+  const double *valtab; // see KArgs
   const int *stop_at;
   int j, rel, cap;
 };
@@ -493,6 +508,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
     for (int i = threadIdx.x; i < 128; i += blockDim.x) sm_tab[i] = s_rc.rewtab[i];
 
   const Code *code_in = reinterpret_cast<const Code *>(a.code_in) + (long long)rep * g.plane_stride;
+  const double *vtab = a.valtab ? a.valtab + ((size_t)rep << (VALTAB_BITS + 1)) : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   Val lmax = Val(0);
 
@@ -509,7 +525,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
         Val v = Val(0);
         if (prow >= 0 && prow < g.rows + 2 * GH) {
           const int col = wrap_col(c0 + cc, g.L);
-          v = val_of_code<Md>(code_in[(long long)prow * g.pitchB + CPAD + col], s_rc, sm_tab);
+          v = val_of_code<Md>(code_in[(long long)prow * g.pitchB + CPAD + col], s_rc, sm_tab, vtab);
         }
         sm_val[(rr + HR) * SMW + cc + HP] = v;
       }
@@ -579,6 +595,93 @@ __device__ __forceinline__ T sel4(int e, T a0, T a1, T a2, T a3) {
   return (e & 2) ? hi : lo;
 }
 
+// per-thread statistics of a launch, handed to step_epilogue (k_step and k_step_lean share the fold)
+struct StepSums {
+  unsigned long long cls_n[4], cls_sn[4], grp[6], n_best, n_best2, n_sel_coop;
+  double sumQ[4], sumQC[4], sumNI, sumR, sumRatio;
+};
+
+// per-CTA partial row, then the last CTA of the replica folds the rows in a fixed order (deterministic)
+// and finishes the public stat row.  The payoff and reward sums of every mode come from exact integer
+// counts: sum of P over a class = ((rc SigmaN / 5 - 5 cost C n) - lo n) / span (spgg.py:256-257,373-377).
+template <class Md>
+__device__ __forceinline__ void step_epilogue(const KArgs &a, int rep, int cta, const RepConst &rc,
+                                              const StepSums &t, double *sm_red, int *s_is_last, bool upd, bool sel) {
+  typedef typename Md::Val Val;
+  constexpr bool kI8 = (sizeof(typename Md::R) == 1);
+  const Geom &g = a.g;
+  double v[NSTAT];
+#pragma unroll
+  for (int z = 0; z < NSTAT; ++z) v[z] = 0.0;
+  v[ST_NC_OLD] = (double)(t.cls_n[2] + t.cls_n[3]);
+  v[ST_N_CD] = (double)t.cls_n[2];
+  v[ST_N_DC] = (double)t.cls_n[1];
+  v[ST_NC_NEW] = (double)(t.cls_n[1] + t.cls_n[3]);
+#pragma unroll
+  for (int z = 0; z < 4; ++z) v[ST_X_SN0 + z] = (double)t.cls_sn[z];
+  // raw class counts ride in these four slots until the fold below
+  v[ST_SUM_P] = (double)t.cls_n[0]; v[ST_SUM_P_C] = (double)t.cls_n[1];
+  v[ST_SUM_P_D] = (double)t.cls_n[2]; v[ST_SUM_WP_P] = (double)t.cls_n[3];
+  v[ST_SUM_RATIO] = t.sumRatio;
+#pragma unroll
+  for (int z = 0; z < 6; ++z) v[ST_GROUP0 + z] = (double)t.grp[z];
+  v[ST_SUM_R] = t.sumR;
+#pragma unroll
+  for (int z = 0; z < 4; ++z) {
+    v[ST_SUM_Q + z] = t.sumQ[z];
+    v[ST_SUM_Q_C + z] = t.sumQC[z];
+  }
+  v[ST_SUM_NI] = t.sumNI;
+  v[ST_N_BEST_POS] = (double)t.n_best;
+  v[ST_N_BEST_2ND] = (double)t.n_best2;
+  v[ST_X_NSEL] = (double)t.n_sel_coop;
+  __syncthreads();
+  block_reduce<NSTAT>(v, sm_red);
+  double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
+  if (threadIdx.x < NSTAT) part[threadIdx.x] = sm_red[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicInc(a.tickets + rep, (unsigned)g.ctas_per_rep - 1u);
+    *s_is_last = (tk == (unsigned)g.ctas_per_rep - 1u);
+  }
+  __syncthreads();
+  if (!*s_is_last) return;
+  __threadfence();
+  fold_partials(a.partials + (long long)rep * g.ctas_per_rep * NSTAT, g.ctas_per_rep, sm_red);
+  if (threadIdx.x == 0) {
+    double *row = a.stats + ((long long)rep * a.cap + a.rel) * NSTAT;
+    double *s = sm_red;
+    if constexpr (kI8) s[ST_SUM_R] *= rc.rq;
+    if (upd) {
+      double Pc[4];
+      const double nc[4] = {s[ST_SUM_P], s[ST_SUM_P_C], s[ST_SUM_P_D], s[ST_SUM_WP_P]};
+      for (int z = 0; z < 4; ++z) {
+        const double C = (z >> 1) ? 1.0 : 0.0;
+        Pc[z] = ((rc.rc * s[ST_X_SN0 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) /
+                rc.span;
+      }
+      s[ST_SUM_P] = Pc[0] + Pc[1] + Pc[2] + Pc[3];
+      s[ST_SUM_P_C] = Pc[2] + Pc[3];
+      s[ST_SUM_P_D] = Pc[0] + Pc[1];
+      s[ST_SUM_WP_P] = rc.wP * s[ST_SUM_P];
+      s[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
+      s[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
+      for (int z = 0; z < 4; ++z) s[ST_SUM_Q_D + z] = s[ST_SUM_Q + z] - s[ST_SUM_Q_C + z];
+      s[ST_GMAX] = (double)reinterpret_cast<const Val *>(a.gmax)[(long long)rep * a.cap + a.rel];
+      for (int z = 0; z < ST_X_SN0; ++z) row[z] = s[z];  // scratch columns stay zero
+    } else {
+      row[ST_SUM_R] = s[ST_SUM_R];
+    }
+    // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405).
+    // Only a handle that owns the whole lattice can tell; strips decide on the host.
+    if (sel && g.wrap_rows) {
+      const double nsel = s[ST_X_NSEL];
+      if (nsel == 0.0 || nsel == (double)g.site_stride) a.stop_at[rep] = a.j + 1;
+    }
+  }
+}
+
 // The general kernel is latency-bound (one site per thread and row, dependent shared-memory stencils):
 // what it needs is resident warps, not registers.  Measured at L=4000 (fp32, int8 R), us per iteration:
 // 1 CTA/SM (190 registers) 1604, 2 CTAs/SM 891, 3 CTAs/SM (80 registers, a few hundred bytes of spills) 718.
@@ -624,6 +727,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
   }
   const RepConst &rc = s_rc;
 
+  const double *vtab = a.valtab ? a.valtab + ((size_t)rep << (VALTAB_BITS + 1)) : nullptr;
   const bool dq = (a.algo == 3);  // Double Q-learning keeps two tables per site: [site][table][s][a]
   QT *Qp = reinterpret_cast<QT *>(a.Q) + (long long)rep * g.site_stride * (dq ? 8 : 4);
   const RT *R_in = reinterpret_cast<const RT *>(a.R_in) + (long long)rep * g.plane_stride;
@@ -663,7 +767,6 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
   unsigned long long n_best = 0, n_best2 = 0, n_sel_coop = 0;
   double sumQ[4] = {0, 0, 0, 0}, sumQC[4] = {0, 0, 0, 0};
   double sumNI = 0.0, sumR = 0.0, sumRatio = 0.0;
-  double sumP = 0, sumPC = 0, sumPD = 0, sumWP = 0, sumRewC = 0, sumRewD = 0;  // fp64 mode
 
   const int n_tiles = g.n_tx * g.n_ty;
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep) {
@@ -679,7 +782,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
       const int nr = g.TR + 2 * M;
       for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
         const int idx = (e / NC - M + HR) * SMW + (e % NC - M + HP);
-        sm_val[idx] = val_of_code<Md>(sm_code[idx], rc, sm_tab);
+        sm_val[idx] = val_of_code<Md>(sm_code[idx], rc, sm_tab, vtab);
       }
     }
     {
@@ -839,17 +942,10 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
               const QT pct = q_mul(q_div(an, q_add(q_add(atd < QT(0) ? -atd : atd, an), (QT)1e-8)), (QT)100.0);
               if constexpr (Md::kFp64) {
                 sumNI += pct;
-                const double P = payoff_f64(code, rc);
-                sumP += P;
-                if (wasC) sumPC += P; else sumPD += P;
-                sumWP += __dmul_rn(rc.wP, P);
-                if (coop) {
-                  sumRewC += vx;
+                pk_sn += (unsigned long long)sigma_n_of_code(code) << (16 * (wasC * 2 + coop));
+                if (coop)
                   sumRatio += __dmul_rn(
                       __ddiv_rn(fabs(__dmul_rn(rc.wR, 0.5)), __dadd_rn(fabs(vx), 1e-9)), 100.0);
-                } else {
-                  sumRewD += vx;
-                }
               } else {
                 tni += pct;
                 pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
@@ -883,17 +979,12 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
               sumNI += __dmul_rn(
                   __ddiv_rn(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)),
                   100.0);                                                                // spgg.py:512
-              const double P = payoff_f64(code, rc);
-              sumP += P;
-              if (wasC) sumPC += P; else sumPD += P;
-              sumWP += __dmul_rn(rc.wP, P);
-              if (coop) {
-                sumRewC += vx;
+              // payoff / reward sums (spgg.py:381-392,419-426) come from exact integer counts at the fold,
+              // as in the fp32 modes: sum P = ((rc SigmaN / 5 - 5 cost C n) - lo n) / span per class
+              pk_sn += (unsigned long long)sigma_n_of_code(code) << (16 * (wasC * 2 + coop));
+              if (coop)
                 sumRatio += __dmul_rn(
                     __ddiv_rn(fabs(__dmul_rn(rc.wR, 0.5)), __dadd_rn(fabs(vx), 1e-9)), 100.0);
-              } else {
-                sumRewD += vx;
-              }
             } else {
               auto next_value = [&](float x0, float x1, bool ex, int rn) -> float {
                 if (a.algo == 0) return fmaxf(x0, x1);
@@ -912,7 +1003,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
               const float td2 = __fsub_rn(__fmaf_rn(rc.gamma_f, next_value(na2, nb2, ex2, rn2), vx), qtd);
               qfin = __fadd_rn(qtd, nu);
               const float an = fabsf(nu);
-              tni += __fdividef(an, fabsf(rc.alpha_f * td2) + an + 1e-8f) * 100.0f;
+              tni = __fmaf_rn(__fdividef(an, __fadd_rn(__fadd_rn(fabsf(__fmul_rn(rc.alpha_f, td2)), an), 1e-8f)), 100.0f, tni);
               pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
               if (rc.has_ratio && coop) tratio += sm_ratio[code >> 1];
             }
@@ -1003,84 +1094,14 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
   }
 
   // ---- per-CTA partial row, then the last CTA of the replica folds them in a fixed order
-  double v[NSTAT];
+  StepSums sums;
 #pragma unroll
-  for (int z = 0; z < NSTAT; ++z) v[z] = 0.0;
-  v[ST_NC_OLD] = (double)(cls_n[2] + cls_n[3]);
-  v[ST_N_CD] = (double)cls_n[2];
-  v[ST_N_DC] = (double)cls_n[1];
-  v[ST_NC_NEW] = (double)(cls_n[1] + cls_n[3]);
-  if constexpr (Md::kFp64) {
-    v[ST_SUM_P] = sumP; v[ST_SUM_P_C] = sumPC; v[ST_SUM_P_D] = sumPD; v[ST_SUM_WP_P] = sumWP;
-    v[ST_SUM_REW_C] = sumRewC; v[ST_SUM_REW_D] = sumRewD;
-  } else {
+  for (int z = 0; z < 4; ++z) { sums.cls_n[z] = cls_n[z]; sums.cls_sn[z] = cls_sn[z]; sums.sumQ[z] = sumQ[z]; sums.sumQC[z] = sumQC[z]; }
 #pragma unroll
-    for (int z = 0; z < 4; ++z) v[ST_X_SN0 + z] = (double)cls_sn[z];
-    // raw class counts ride in these four slots until the fold below
-    v[ST_SUM_P] = (double)cls_n[0]; v[ST_SUM_P_C] = (double)cls_n[1];
-    v[ST_SUM_P_D] = (double)cls_n[2]; v[ST_SUM_WP_P] = (double)cls_n[3];
-  }
-  v[ST_SUM_RATIO] = sumRatio;
-#pragma unroll
-  for (int z = 0; z < 6; ++z) v[ST_GROUP0 + z] = (double)grp[z];
-  v[ST_SUM_R] = sumR;
-#pragma unroll
-  for (int z = 0; z < 4; ++z) {
-    v[ST_SUM_Q + z] = sumQ[z];
-    v[ST_SUM_Q_C + z] = sumQC[z];
-  }
-  v[ST_SUM_NI] = sumNI;
-  v[ST_N_BEST_POS] = (double)n_best;
-  v[ST_N_BEST_2ND] = (double)n_best2;
-  v[ST_X_NSEL] = (double)n_sel_coop;
-  __syncthreads();
-  block_reduce<NSTAT>(v, sm_red);
-  double *part = a.partials + ((long long)rep * g.ctas_per_rep + cta) * NSTAT;
-  if (threadIdx.x < NSTAT) part[threadIdx.x] = sm_red[threadIdx.x];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicInc(a.tickets + rep, (unsigned)g.ctas_per_rep - 1u);
-    s_is_last = (t == (unsigned)g.ctas_per_rep - 1u);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  fold_partials(a.partials + (long long)rep * g.ctas_per_rep * NSTAT, g.ctas_per_rep, sm_red);
-  if (threadIdx.x == 0) {
-    double *row = a.stats + ((long long)rep * a.cap + a.rel) * NSTAT;
-    double *s = sm_red;
-    if constexpr (kI8) s[ST_SUM_R] *= rc.rq;
-    if (upd) {
-      if constexpr (!Md::kFp64) {
-        // exact-count payoff sums per class: P = ((rc*SN/5 - 5*cost*C) - lo)/span
-        double Pc[4];
-        const double nc[4] = {s[ST_SUM_P], s[ST_SUM_P_C], s[ST_SUM_P_D], s[ST_SUM_WP_P]};
-        for (int z = 0; z < 4; ++z) {
-          const double C = (z >> 1) ? 1.0 : 0.0;
-          Pc[z] = ((rc.rc * s[ST_X_SN0 + z] / 5.0 - 5.0 * rc.cost * C * nc[z]) - rc.lo * nc[z]) /
-                  rc.span;
-        }
-        s[ST_SUM_P] = Pc[0] + Pc[1] + Pc[2] + Pc[3];
-        s[ST_SUM_P_C] = Pc[2] + Pc[3];
-        s[ST_SUM_P_D] = Pc[0] + Pc[1];
-        s[ST_SUM_WP_P] = rc.wP * s[ST_SUM_P];
-        s[ST_SUM_REW_C] = rc.wP * (Pc[1] + Pc[3]) + rc.wR * 0.5 * (nc[1] + nc[3]);
-        s[ST_SUM_REW_D] = rc.wP * (Pc[0] + Pc[2]);
-      }
-      for (int z = 0; z < 4; ++z) s[ST_SUM_Q_D + z] = s[ST_SUM_Q + z] - s[ST_SUM_Q_C + z];
-      s[ST_GMAX] = (double)reinterpret_cast<const Val *>(a.gmax)[(long long)rep * a.cap + a.rel];
-      for (int z = 0; z < ST_X_SN0; ++z) row[z] = s[z];  // scratch columns stay zero
-    } else {
-      row[ST_SUM_R] = s[ST_SUM_R];
-    }
-    // uniform lattice after the action just chosen -> the next iteration breaks (spgg.py:405).
-    // Only a handle that owns the whole lattice can tell; strips decide on the host.
-    if (sel && g.wrap_rows) {
-      const double nsel = s[ST_X_NSEL];
-      if (nsel == 0.0 || nsel == (double)g.site_stride) a.stop_at[rep] = a.j + 1;
-    }
-  }
+  for (int z = 0; z < 6; ++z) sums.grp[z] = grp[z];
+  sums.n_best = n_best; sums.n_best2 = n_best2; sums.n_sel_coop = n_sel_coop;
+  sums.sumNI = sumNI; sums.sumR = sumR; sums.sumRatio = sumRatio;
+  step_epilogue<Md>(a, rep, cta, rc, sums, sm_red, &s_is_last, upd, sel);
 }
 
 // strip decomposition: boundary rows <-> contiguous halo buffers --------------------

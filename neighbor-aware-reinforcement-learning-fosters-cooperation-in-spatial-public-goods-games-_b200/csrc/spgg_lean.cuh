@@ -1,0 +1,580 @@
+// Lean update kernel of the general path: the Q-learning iteration of k_step (spgg_kernels.cuh) for the
+// lattices the TMA fast path does not take - reference precision (fp64 Q and R, spgg.py:121,129), fp32
+// reputations, lattice sides that are not multiples of 32 - with the same thread <-> site mapping, the same
+// arithmetic in the same order and therefore the same results bit for bit, statistics included
+// (tests/test_gpu_lean.py compares the two with SPGG_NO_LEAN=1).
+//
+// k_step carries every TD rule, the replay of up to three draw streams and the select-only / update-only
+// launches behind runtime switches; ncu counted 570 instructions per site for its select-only launch alone
+// (profiles/r02_fp64_lean.md).  What this kernel does differently:
+//   * Q-learning and "update" are compile-time facts (the host launches it for algo 0, do_update = 1);
+//   * the reward of an fp64 code is a table lookup (KArgs::valtab, built once per handle by k_build_valtab
+//     with payoff_f64 / reward_f64 themselves) instead of an fp64 division per staged site;
+//   * tiles are staged row by row (a warp per staged row, no division per element), the code -> reward pass
+//     is fused into the code load, ghost columns are read instead of wrapped;
+//   * the Q entries of the four sites a thread owns in a row (and their replayed draws) are loaded before
+//     the first of them is processed, and the Q rows of the CTA's next tile are prefetched into L2;
+//   * interior tiles store with plain stores (no ghost-copy tests per cell);
+//   * the divisions of the neighbour-aware term and of its statistic are skipped where the numerator is an
+//     exact zero (the quotient is that zero), which is most sites once domains have formed;
+//   * the reputation state compares the sum with zero instead of dividing it by the neighbourhood size.
+#pragma once
+#include "spgg_kernels.cuh"
+
+namespace spgg {
+
+// {reward, ratio statistic} of every fp64 reward code (index code >> 1), reference operation order
+// (spgg.py:256-257,373-377,424-427; the ratio of spgg.py:430 for cooperating codes)
+__global__ void k_build_valtab(const RepConst *rc_all, double *tab) {
+  const int rep = blockIdx.y;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (1u << VALTAB_BITS)) return;
+  const RepConst &rc = rc_all[rep];
+  const uint32_t code = idx << 1;
+  double v = 0.0, ratio = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) ok = ok && (((code >> (15 - 3 * q)) & 7u) <= 5u);
+  if (ok) {
+    v = reward_f64(code, payoff_f64(code, rc), rc);
+    if ((code >> 1) & 1u)
+      ratio = __dmul_rn(__ddiv_rn(fabs(__dmul_rn(rc.wR, 0.5)), __dadd_rn(fabs(v), 1e-9)), 100.0);
+  }
+  double *dst = tab + (((size_t)rep << VALTAB_BITS) + idx) * 2;
+  dst[0] = v;
+  dst[1] = ratio;
+}
+
+template <bool B>
+struct BoolC { static constexpr bool value = B; };
+
+// sign of the neighbourhood mean (spgg.py:292-307) without the division: x / n > 0 <=> x > 0 unless the
+// quotient underflows, which needs |x| below 1e-300 - there the division is done
+template <class RT, int M>
+__device__ __forceinline__ int rep_state_lean(const RT *smR, int sr, int sc) {
+  constexpr int NK = (M == 2) ? 12 : 4;
+  if constexpr (sizeof(RT) == 1) {
+    return rep_state<RT, M>(smR, sr, sc);
+  } else if constexpr (sizeof(RT) == 4) {
+    float acc = smR[sr * SMW + sc];
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      acc = __fadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
+    if (fabsf(acc) > 1e-30f) return acc > 0.0f;
+    return __fdiv_rn(acc, (float)(NK + 1)) > 0.0f;
+  } else {
+    double acc = smR[sr * SMW + sc];
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      acc = __dadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
+    if (fabs(acc) > 1e-300) return acc > 0.0;
+    return __ddiv_rn(acc, (double)(NK + 1)) > 0.0;
+  }
+}
+
+// Stages the halo'd planes of a tile with every global load of a thread in flight at once (the general
+// kernel's element loops expose one memory round trip per element: ncu, profiles/r02_fp64_lean.md).
+// A warp owns the staged rows r = warp, warp + nw, warp + 2 nw of rows -2 .. TR+1:
+//   phase A  raw loads: reward codes and reputations (halo M; ghost columns and ghost rows of the planes hold
+//            the periodic images, store_cell keeps GC >= M of them current) and the six strategy words of a row
+//   phase B  stores of codes / reputations / cooperator flags, and the reward-table lookups (fp64) of all rows
+//   phase C  reward stores
+// STEP = false stages the rewards only (k_gmax_lean).
+template <class Md, int M, bool STEP>
+__device__ __forceinline__ void stage_tile(const Geom &g, int r0, int c0, const typename Md::Code *code_in,
+                                           const typename Md::R *R_in, const uint32_t *S_in, const RepConst &rc,
+                                           const float *sm_tab, const double *vtab, typename Md::Val *sm_val,
+                                           typename Md::Code *sm_code, typename Md::R *sm_R, uint8_t *sm_C) {
+  typedef typename Md::Code Code;
+  typedef typename Md::R RT;
+  typedef typename Md::Val Val;
+  constexpr int NQ = (TC + 4 + 31) / 32, MAXIT = 3;   // (TR + 4) rows / nw warps <= 3 for every geometry spgg_create picks
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int cmax = g.L + GC;                       // first column without a current image
+  // strategy words can be taken whole where no column of the halo'd tile wraps
+  const bool wordpath = STEP && c0 >= 32 && c0 + TC + 2 <= g.L;
+  Code cv[MAXIT][NQ];
+  RT rv[MAXIT][NQ];
+  uint32_t sw[MAXIT];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int r = warp + it * nw, rr = r - 2, prow = r0 + rr + GH;
+    const bool rowok = r < g.TR + 4 && prow < g.rows + 2 * GH;
+    const bool in_cr = rowok && rr >= -M && rr < g.TR + M;
+    const long long rowoff = (long long)prow * g.pitchB + CPAD + c0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int cc = q * 32 + lane - 2;
+      const bool ok = in_cr && cc >= -M && cc < TC + M && c0 + cc < cmax;
+      cv[it][q] = ok ? code_in[rowoff + cc] : Code(0);
+      if constexpr (STEP) rv[it][q] = ok ? R_in[rowoff + cc] : RT(0);
+    }
+    if constexpr (STEP)
+      sw[it] = (wordpath && rowok && lane < 6) ? S_in[(long long)prow * g.pitchW + WPAD + (c0 >> 5) - 1 + lane] : 0u;
+  }
+  Val vv[MAXIT][NQ];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int r = warp + it * nw, rr = r - 2;
+    const bool rowact = r < g.TR + 4;
+    const bool in_cr = rowact && rr >= -M && rr < g.TR + M;
+    const int base = (rr + HR) * SMW + HP;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int cc = q * 32 + lane - 2;
+      if constexpr (Md::kFp64) vv[it][q] = __ldg(vtab + 2 * (size_t)(cv[it][q] >> 1));   // code 0 is a valid entry
+      else vv[it][q] = sm_tab[cv[it][q] >> 1];
+      if constexpr (STEP) {
+        if (in_cr && cc >= -M && cc < TC + M) {
+          sm_code[base + cc] = cv[it][q];
+          sm_R[base + cc] = rv[it][q];
+        }
+        // cooperator flag of the cell: bit cc & 31 of word (cc + 32) >> 5 of the six (c0 is a multiple of 32)
+        const uint32_t w = __shfl_sync(0xffffffffu, sw[it], (cc + 32) >> 5);
+        const bool rowok = r0 + rr + GH < g.rows + 2 * GH;      // rows below the ghost rows read as defectors
+        if (wordpath && rowact && cc < TC + 2) sm_C[base + cc] = rowok ? (uint8_t)((~w >> (cc & 31)) & 1u) : (uint8_t)0;
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int r = warp + it * nw, rr = r - 2;
+    const bool in_cr = r < g.TR + 4 && rr >= -M && rr < g.TR + M;
+    const int base = (rr + HR) * SMW + HP;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int cc = q * 32 + lane - 2;
+      if (in_cr && cc >= -M && cc < TC + M) sm_val[base + cc] = vv[it][q];
+    }
+  }
+  if constexpr (STEP) {
+    if (!wordpath) load_coop_tile(sm_C, S_in, g, r0, c0, g.TR);   // edge tile columns: per-cell wrap
+  }
+}
+
+// Lattice-global max |reward difference| over neighbour pairs (spgg.py:486-488), lean version of k_gmax:
+// tiles staged row by row with the rewards looked up while they land, and every unordered pair taken once
+// (|x - y| == |y - x| exactly): from each site towards (i+1,j), (i,j+1) and, second order, (i+2,j), (i,j+2),
+// (i+1,j+1), (i+1,j-1).  The maximum of a set does not depend on the order: same value as k_gmax.
+template <class Md, int M>
+__global__ void __launch_bounds__(MAX_THREADS) k_gmax_lean(GArgs a) {
+  typedef typename Md::Code Code;
+  typedef typename Md::Val Val;
+  const Geom &g = a.g;
+  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  Val *sm_val = reinterpret_cast<Val *>(smem);
+  float *sm_tab = reinterpret_cast<float *>(smem + align_up(sizeof(Val) * (g.TR + 2 * HR) * SMW, 16));
+  __shared__ RepConst s_rc;
+  for (int i = threadIdx.x; i < (int)(sizeof(RepConst) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  __syncthreads();
+  if (!Md::kFp64)
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) sm_tab[i] = s_rc.rewtab[i];
+
+  const Code *code_in = reinterpret_cast<const Code *>(a.code_in) + (long long)rep * g.plane_stride;
+  const double *vtab = a.valtab ? a.valtab + ((size_t)rep << (VALTAB_BITS + 1)) : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  Val lmax = Val(0);
+  // one of each +/- pair of c_off: neighbour (i-dx, j-dy)
+  constexpr int NP = (M == 2) ? 6 : 2;
+  constexpr int kPair[6] = {1, 3, 5, 7, 11, 10};
+
+  const int n_tiles = g.n_tx * g.n_ty;
+  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep) {
+    const int ty = tile / g.n_tx, tx = tile - ty * g.n_tx;
+    const int r0 = ty * g.TR, c0 = tx * TC;
+    __syncthreads();
+    stage_tile<Md, M, false>(g, r0, c0, code_in, nullptr, nullptr, s_rc, sm_tab, vtab, sm_val, nullptr, nullptr, nullptr);
+    __syncthreads();
+    for (int rr = warp; rr < g.TR; rr += nw) {
+      if (r0 + rr >= g.rows) break;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int cc = k4 * 32 + lane;
+        if (c0 + cc >= g.L) continue;
+        const int sr = rr + HR, sc = cc + HP;
+        const Val vx = sm_val[sr * SMW + sc];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          const Val vk = sm_val[(sr - c_off[kPair[k]][0]) * SMW + (sc - c_off[kPair[k]][1])];
+          Val d;
+          if constexpr (Md::kFp64) d = fabs(__dsub_rn(vk, vx));
+          else d = fabsf(__fsub_rn(vk, vx));
+          lmax = d > lmax ? d : lmax;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const Val other = __shfl_down_sync(0xffffffffu, lmax, o);
+    lmax = other > lmax ? other : lmax;
+  }
+  __shared__ Val s_wmax[MAX_THREADS / 32];
+  if (lane == 0) s_wmax[warp] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Val m = s_wmax[0];
+    for (int w = 1; w < nw; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
+    Val *dst = reinterpret_cast<Val *>(a.gmax) + (long long)rep * a.cap + a.rel;
+    if constexpr (Md::kFp64)
+      atomicMax(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)__double_as_longlong(m));
+    else
+      atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(m));
+  }
+}
+
+#ifndef SPGG_LEAN_MINBLOCKS
+#define SPGG_LEAN_MINBLOCKS 2
+#endif
+
+template <class Md, int M, bool ACTION, bool REPLAY>
+__global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(KArgs a) {
+  typedef typename Md::Q QT;
+  typedef typename Md::R RT;
+  typedef typename Md::Code Code;
+  typedef typename Md::Val Val;
+  constexpr int NK = (M == 2) ? 12 : 4;
+  constexpr bool kI8 = (sizeof(RT) == 1);
+  const Geom &g = a.g;
+  const int rep = blockIdx.x / g.ctas_per_rep, cta = blockIdx.x % g.ctas_per_rep;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int stop = a.stop_at[rep];
+  if (stop >= 0 && a.j > stop) return;
+  constexpr bool upd = true;
+  const bool sel = (a.do_select != 0) && !(stop >= 0 && a.j == stop);
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout<Md> lay(g.TR);
+  Val *sm_val = reinterpret_cast<Val *>(smem + lay.off_val);
+  RT *sm_R = reinterpret_cast<RT *>(smem + lay.off_R);
+  Code *sm_code = reinterpret_cast<Code *>(smem + lay.off_code);
+  uint8_t *sm_C = smem + lay.off_C;
+  uint8_t *sm_N = smem + lay.off_N;
+  float *sm_tab = reinterpret_cast<float *>(smem + lay.off_tab);
+  float *sm_ratio = sm_tab + 128;
+  double *sm_red = reinterpret_cast<double *>(smem + lay.off_red);
+  __shared__ RepConst s_rc;
+  __shared__ int s_is_last;
+
+  for (int i = threadIdx.x; i < (int)(sizeof(RepConst) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t *>(&s_rc)[i] = reinterpret_cast<const uint32_t *>(a.rc + rep)[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    sm_tab[i] = s_rc.rewtab[i];
+    sm_ratio[i] = s_rc.ratiotab[i];
+  }
+  const RepConst &rc = s_rc;
+  const double *vtab = a.valtab ? a.valtab + ((size_t)rep << (VALTAB_BITS + 1)) : nullptr;
+
+  QT *Qp = reinterpret_cast<QT *>(a.Q) + (long long)rep * g.site_stride * 4;
+  const RT *R_in = reinterpret_cast<const RT *>(a.R_in) + (long long)rep * g.plane_stride;
+  RT *R_out = reinterpret_cast<RT *>(a.R_out) + (long long)rep * g.plane_stride;
+  const Code *code_in = reinterpret_cast<const Code *>(a.code_in) + (long long)rep * g.plane_stride;
+  Code *code_out = reinterpret_cast<Code *>(a.code_out) + (long long)rep * g.plane_stride;
+  const uint32_t *S_in = a.S_in + (long long)rep * g.bits_stride;
+  uint32_t *S_out = a.S_out + (long long)rep * g.bits_stride;
+
+  Val inv_den = Val(0), den = Val(1);
+  {
+    const Val gm = reinterpret_cast<const Val *>(a.gmax)[(long long)rep * a.cap + a.rel];
+    if constexpr (Md::kFp64) den = __dadd_rn(gm, rc.leps);  // spgg.py:489 denominator
+    else inv_den = __fdiv_rn(1.0f, __fadd_rn(gm, rc.leps_f));
+  }
+  const long long tab_idx = (long long)(a.rel + 1) * g.n_rep + rep;
+  const uint32_t thr = sel ? a.thr_tab[tab_idx] : 0u;
+  const double eps = (sel && REPLAY) ? a.eps_tab[tab_idx] : 0.0;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  // per-thread statistics, accumulated in k_step's order (site by site: tile, row, k4)
+  // (32-bit counters: a thread sees at most a few 10^5 sites per launch, SigmaN <= 25 each)
+  uint32_t cls_n[4] = {0, 0, 0, 0}, cls_sn[4] = {0, 0, 0, 0};
+  uint32_t grp[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t n_best = 0, n_best2 = 0, n_sel_coop = 0;
+  double sumQ[4] = {0, 0, 0, 0}, sumQC[4] = {0, 0, 0, 0};
+  double sumNI = 0.0, sumR = 0.0, sumRatio = 0.0;
+
+  const int n_tiles = g.n_tx * g.n_ty;
+  for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep) {
+    const int ty = tile / g.n_tx, tx = tile - ty * g.n_tx;
+    const int r0 = ty * g.TR, c0 = tx * TC;
+    const bool full = (c0 + TC <= g.L) && (r0 + g.TR <= g.rows);
+    // no cell of this tile has a periodic copy (ghost column / ghost row / ghost word)
+    const bool interior = full && c0 >= GC && c0 + TC <= g.L - GC &&
+                          (!g.wrap_rows || (r0 >= GH && r0 + g.TR <= g.rows - GH));
+    __syncthreads();
+    {  // the Q rows of this CTA's next tile on their way into L2 while this tile is computed
+      const int nt = tile + g.ctas_per_rep;
+      if (nt < n_tiles) {
+        const int nty = nt / g.n_tx, ntx = nt - nty * g.n_tx;
+        const int nrow = nty * g.TR, ncol = ntx * TC;
+        constexpr int kLineSites = 128 / (int)(4 * sizeof(QT));      // sites per 128-byte line
+        const int lines = TC / kLineSites;
+        for (int e = threadIdx.x; e < g.TR * lines; e += blockDim.x) {
+          const int rr = e / lines, cs = ncol + (e - rr * lines) * kLineSites;
+          if (nrow + rr < g.rows && cs < g.L)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Qp + ((long long)(nrow + rr) * g.L + cs) * 4));
+        }
+      }
+    }
+    // ---- stage the halo'd tiles: reward codes (+ their rewards), reputations, cooperator flags
+    stage_tile<Md, M, true>(g, r0, c0, code_in, R_in, S_in, rc, sm_tab, vtab, sm_val, sm_code, sm_R, sm_C);
+    __syncthreads();
+    {
+      // N = cooperators in the 5-site group centred on each site (spgg.py:23-36) of S_j, tile + one-site ring
+      const int nr = g.TR + 2;
+      for (int r = warp; r < nr; r += nw) {
+        const int base = (r - 1 + HR) * SMW + HP;
+#pragma unroll
+        for (int q = 0; q < (TC + 2 + 31) / 32; ++q) {
+          const int cc = q * 32 + lane - 1;
+          if (cc < TC + 1) {
+            const int idx = base + cc;
+            sm_N[idx] = (uint8_t)(sm_C[idx] + sm_C[idx + SMW] + sm_C[idx - SMW] + sm_C[idx + 1] + sm_C[idx - 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    unsigned pk_n = 0;
+    unsigned long long pk_sn = 0, pk_grp = 0;
+    float tq[4] = {0.f, 0.f, 0.f, 0.f}, tqc[4] = {0.f, 0.f, 0.f, 0.f};
+    float tni = 0.f, tratio = 0.f, trf = 0.f;
+    int tri = 0;
+
+    auto do_row = [&](auto fullc, auto interiorc, int rr) {
+      constexpr bool FULL = decltype(fullc)::value;
+      constexpr bool INTERIOR = decltype(interiorc)::value;
+      const int i = r0 + rr;
+      const int sr = rr + HR;
+      uint32_t w4[4] = {0, 0, 0, 0};
+      if (sel && !REPLAY) {
+        // counter = (column / 4, global row, iteration, 0), as in k_step
+        uint32_t wc[4];
+        philox4x32_10((uint32_t)((c0 >> 2) + lane), (uint32_t)(g.row0 + i), (uint32_t)(a.j + 1), 0u,
+                      rc.seed_lo, rc.seed_hi, wc);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int src = 8 * k4 + (lane >> 2);
+          const uint32_t x0 = __shfl_sync(0xffffffffu, wc[0], src), x1 = __shfl_sync(0xffffffffu, wc[1], src);
+          const uint32_t x2 = __shfl_sync(0xffffffffu, wc[2], src), x3 = __shfl_sync(0xffffffffu, wc[3], src);
+          w4[k4] = sel4<uint32_t>(lane & 3, x0, x1, x2, x3);
+        }
+      }
+      // ---- everything that comes from global memory for the four sites, before the first is processed
+      QT q[4][4];
+      double ru[4] = {0, 0, 0, 0};
+      uint8_t rb[4] = {0, 0, 0, 0};
+      double rat[4] = {0, 0, 0, 0};   // fp64: ratio statistic of the site's code (second table column)
+      const long long site_row = (long long)i * g.L + c0 + lane;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const bool valid = FULL || (c0 + 32 * k4 + lane < g.L);
+        const long long site = site_row + 32 * k4;
+        if (valid) {
+          if constexpr (Md::kFp64) {
+            const double2 lo2 = reinterpret_cast<const double2 *>(Qp)[site * 2];
+            const double2 hi2 = reinterpret_cast<const double2 *>(Qp)[site * 2 + 1];
+            q[k4][0] = lo2.x; q[k4][1] = lo2.y; q[k4][2] = hi2.x; q[k4][3] = hi2.y;
+          } else {
+            const float4 v = reinterpret_cast<const float4 *>(Qp)[site];
+            q[k4][0] = v.x; q[k4][1] = v.y; q[k4][2] = v.z; q[k4][3] = v.w;
+          }
+          if constexpr (REPLAY) {
+            if (sel) { ru[k4] = a.u[site]; rb[k4] = a.b[site]; }
+          }
+          if constexpr (Md::kFp64)
+            rat[k4] = __ldg(vtab + 2 * (size_t)(sm_code[sr * SMW + 32 * k4 + lane + HP] >> 1) + 1);   // 0 for defecting codes
+        } else {
+          q[k4][0] = q[k4][1] = q[k4][2] = q[k4][3] = QT(0);
+        }
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int cc = k4 * 32 + lane;
+        const int col = c0 + cc;
+        const bool valid = FULL || (col < g.L);
+        const int sc = cc + HP;
+        const int sidx = sr * SMW + sc;
+        int a_new = 0;
+        if (valid) {
+          const long long site = site_row + 32 * k4;
+          QT q0_ = q[k4][0], q1_ = q[k4][1], q2_ = q[k4][2], q3_ = q[k4][3];
+          const RT r_old = sm_R[sidx];
+          const int Ccur = sm_C[sidx];
+          // post-action state of iteration j == pre-action state of iteration j+1 (spgg.py:409/423)
+          const int s_new = ACTION ? Ccur : rep_state_lean<RT, M>(sm_R, sr, sc);
+          if constexpr (kI8) tri += (int)r_old;
+          else if constexpr (sizeof(RT) == 4) trf += r_old;
+          else sumR += r_old;
+
+          const Code code = sm_code[sidx];
+          const int s = code & 1u, coop = (code >> 1) & 1u, wasC = (code >> 2) & 1u;
+          const int act = coop ^ 1;
+          const Val vx = sm_val[sidx];
+          // neighbour-aware term inputs: spgg.py:486-494 (first arg-max wins)
+          Val best = Val(0);
+          int bidx = sidx, kstar = 0;
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            const int nidx = (sr - c_off[k][0]) * SMW + (sc - c_off[k][1]);
+            const Val vk = sm_val[nidx];
+            Val d;
+            if constexpr (Md::kFp64) d = __dsub_rn(vk, vx);
+            else d = __fsub_rn(vk, vx);
+            if (k == 0 || d > best) { best = d; bidx = nidx; kstar = k; }
+          }
+          const bool same = (((sm_code[bidx] >> 1) & 1u) == (unsigned)coop);
+          const int e = 2 * s + act;
+          const QT qe = sel4<QT>(e, q0_, q1_, q2_, q3_);
+          const QT na = s_new ? q2_ : q0_, nb = s_new ? q3_ : q1_;  // pre-update row of s'
+          QT qfin;
+          if constexpr (Md::kFp64) {
+            const double mx = fmax(na, nb);                                              // algorithms.py:125
+            const double td = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, mx)), qe);     // algorithms.py:128
+            const double qtd = __dadd_rn(qe, __dmul_rn(rc.alpha, td));                   // algorithms.py:131
+            const double num = __dmul_rn(rc.kappa, fmax(0.0, best));
+            // an exact zero over a positive denominator is that zero: no division for the sites without a
+            // better neighbour
+            const double lam = (num == 0.0 && den > 0.0) ? num : __ddiv_rn(num, den);    // spgg.py:489
+            const double nu = same ? lam : -lam;                                         // spgg.py:494-495
+            const double na2 = (s_new == s && act == 0) ? qtd : na;
+            const double nb2 = (s_new == s && act == 1) ? qtd : nb;
+            const double td2 = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, fmax(na2, nb2))), qtd);
+            qfin = __dadd_rn(qtd, nu);                                                   // spgg.py:509
+            const double an = fabs(nu);
+            if (an != 0.0)                                                               // 0 / (x + 1e-8) * 100 adds +0
+              sumNI += __dmul_rn(
+                  __ddiv_rn(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)), 100.0);  // spgg.py:512
+            pk_sn += (unsigned long long)sigma_n_of_code(code) << (16 * (wasC * 2 + coop));
+            if (coop) sumRatio += rat[k4];
+          } else {
+            const float mx = fmaxf(na, nb);
+            const float td = __fsub_rn(__fmaf_rn(rc.gamma_f, mx, vx), qe);
+            const float qtd = __fmaf_rn(rc.alpha_f, td, qe);
+            const float lam = __fmul_rn(__fmul_rn(rc.kappa_f, fmaxf(0.0f, best)), inv_den);
+            const float nu = same ? lam : -lam;
+            const float na2 = (s_new == s && act == 0) ? qtd : na;
+            const float nb2 = (s_new == s && act == 1) ? qtd : nb;
+            const float td2 = __fsub_rn(__fmaf_rn(rc.gamma_f, fmaxf(na2, nb2), vx), qtd);
+            qfin = __fadd_rn(qtd, nu);
+            const float an = fabsf(nu);
+            tni = __fmaf_rn(__fdividef(an, __fadd_rn(__fadd_rn(fabsf(__fmul_rn(rc.alpha_f, td2)), an), 1e-8f)), 100.0f, tni);
+            pk_sn += (unsigned long long)(code >> 3) << (16 * (wasC * 2 + coop));
+            if (rc.has_ratio && coop) tratio += sm_ratio[code >> 1];
+          }
+          q0_ = (e == 0) ? qfin : q0_;
+          q1_ = (e == 1) ? qfin : q1_;
+          q2_ = (e == 2) ? qfin : q2_;
+          q3_ = (e == 3) ? qfin : q3_;
+          pk_n += 1u << (8 * (wasC * 2 + coop));
+          if (best > Val(0)) { n_best += 1u; n_best2 += (kstar >= 4); }
+          pk_grp += 1ull << (10 * (5 - (int)sm_N[sidx]));                                // spgg.py:586-592
+          if constexpr (Md::kFp64) {
+            sumQ[0] += q0_; sumQ[1] += q1_; sumQ[2] += q2_; sumQ[3] += q3_;
+            if (wasC) { sumQC[0] += q0_; sumQC[1] += q1_; sumQC[2] += q2_; sumQC[3] += q3_; }
+          } else {
+            const float m = wasC ? 1.0f : 0.0f;
+            tq[0] += q0_; tq[1] += q1_; tq[2] += q2_; tq[3] += q3_;
+            tqc[0] = fmaf(m, q0_, tqc[0]); tqc[1] = fmaf(m, q1_, tqc[1]);
+            tqc[2] = fmaf(m, q2_, tqc[2]); tqc[3] = fmaf(m, q3_, tqc[3]);
+          }
+
+          if (sel) {
+            int explore, rnd;
+            if constexpr (REPLAY) {
+              explore = ru[k4] < eps;  // algorithms.py:105
+              rnd = rb[k4];            // algorithms.py:108
+            } else {
+              explore = (w4[k4] >> 8) < thr;
+              rnd = (int)(w4[k4] & 1u);
+            }
+            const QT ga = s_new ? q2_ : q0_, gb = s_new ? q3_ : q1_;
+            const int greedy = (gb > ga) ? 1 : 0;  // np.argmax, tie -> 0   algorithms.py:107
+            a_new = explore ? rnd : greedy;        // algorithms.py:109
+            n_sel_coop += (a_new == 0);
+            RT r_new;                              // spgg.py:321-323
+            if constexpr (kI8) {
+              int t = (int)r_old + (a_new == 0 ? rc.gain_i : -rc.loss_i);
+              t = max(t, rc.rmin_i);
+              t = min(t, rc.rmax_i);
+              r_new = (RT)t;
+            } else if constexpr (sizeof(RT) == 4) {
+              const float t = __fadd_rn(r_old, a_new == 0 ? rc.gainC_f : -rc.lossD_f);
+              r_new = fminf(fmaxf(t, rc.rmin_f), rc.rmax_f);
+            } else {
+              const double t = __dadd_rn(r_old, a_new == 0 ? rc.gainC : -rc.lossD);
+              r_new = fmin(fmax(t, rc.rmin), rc.rmax);
+            }
+            const int n5[5] = {sm_N[sidx], sm_N[sidx - SMW], sm_N[sidx + SMW], sm_N[sidx - 1], sm_N[sidx + 1]};
+            const Code cnew = pack_code<Md>(n5, Ccur, a_new ^ 1, s_new);
+            if constexpr (INTERIOR) {
+              const long long o = (long long)(i + GH) * g.pitchB + CPAD + col;
+              code_out[o] = cnew;
+              R_out[o] = r_new;
+            } else {
+              store_cell<Code>(code_out, g, i, col, cnew);
+              store_cell<RT>(R_out, g, i, col, r_new);
+            }
+          }
+          if constexpr (Md::kFp64) {
+            reinterpret_cast<double2 *>(Qp)[site * 2] = make_double2(q0_, q1_);
+            reinterpret_cast<double2 *>(Qp)[site * 2 + 1] = make_double2(q2_, q3_);
+          } else {
+            reinterpret_cast<float4 *>(Qp)[site] = make_float4(q0_, q1_, q2_, q3_);
+          }
+        }
+        if (sel) {
+          const uint32_t word = __ballot_sync(0xffffffffu, valid && a_new);
+          const int wi = (c0 >> 5) + k4;
+          if (lane == 0) {
+            if constexpr (INTERIOR) S_out[(long long)(i + GH) * g.pitchW + WPAD + wi] = word;
+            else if (wi * 32 < g.L) store_bits_word(S_out, g, i, wi, word);
+          }
+        }
+      }
+    };
+
+    if (interior) {
+      for (int rr = warp; rr < g.TR; rr += nw) do_row(BoolC<true>{}, BoolC<true>{}, rr);
+    } else {
+      for (int rr = warp; rr < g.TR; rr += nw) {
+        if (r0 + rr >= g.rows) break;
+        do_row(BoolC<false>{}, BoolC<false>{}, rr);
+      }
+    }
+    // flush the per-tile packed counters
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+      cls_n[z] += (pk_n >> (8 * z)) & 0xffu;
+      cls_sn[z] += (uint32_t)((pk_sn >> (16 * z)) & 0xffffull);
+      sumQ[z] += (double)tq[z];
+      sumQC[z] += (double)tqc[z];
+    }
+#pragma unroll
+    for (int z = 0; z < 6; ++z) grp[z] += (uint32_t)((pk_grp >> (10 * z)) & 0x3ffull);
+    sumNI += (double)tni;
+    sumRatio += (double)tratio;
+    sumR += (double)tri + (double)trf;
+  }
+
+  StepSums sums;
+#pragma unroll
+  for (int z = 0; z < 4; ++z) { sums.cls_n[z] = cls_n[z]; sums.cls_sn[z] = cls_sn[z]; sums.sumQ[z] = sumQ[z]; sums.sumQC[z] = sumQC[z]; }
+#pragma unroll
+  for (int z = 0; z < 6; ++z) sums.grp[z] = grp[z];
+  sums.n_best = n_best; sums.n_best2 = n_best2; sums.n_sel_coop = n_sel_coop;
+  sums.sumNI = sumNI; sums.sumR = sumR; sums.sumRatio = sumRatio;
+  step_epilogue<Md>(a, rep, cta, rc, sums, sm_red, &s_is_last, upd, sel);
+}
+
+}  // namespace spgg
