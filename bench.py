@@ -452,7 +452,7 @@ def measure_extras(L, peak, anchor=True):
     }
     for name, (p, prec, bps) in cases.items():
         try:
-            us, desc = measure_iteration(p, prec)
+            us, desc = measure_iteration(p, prec, n_warm=3, n_iter=24)   # one chunk: its select-only first launch is 1/24 of it
             n = p["L"] * p["L"]
             variants[name] = {"L": p["L"], "us_per_iteration": us, "site_updates_per_s": n / (us * 1e-6),
                               "bytes_per_site": bps, "roofline_frac": bps * n / (us * 1e-6) / 1e9 / peak,

@@ -537,6 +537,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   int occ = 1;
   h->lean = !h->fast && p0.algorithm == 0 && getenv("SPGG_NO_LEAN") == nullptr;
+  if (h->lean) h->smem_step = step_smem(h->mode, LEAN_TR_MAX);   // k_step_lean addresses the 16-row layout
   h->lean_gmax = getenv("SPGG_NO_LEAN") == nullptr;
   for (int replay = 0; replay < 2; ++replay) {
     step_fn_t f = pick_step(h->mode, h->M, h->action, replay);

@@ -262,6 +262,21 @@ __device__ __forceinline__ typename Md::Val val_of_code(typename Md::Code code, 
   }
 }
 
+// num / den, correctly rounded, without __ddiv_rn's slow path for an exactly-zero numerator over a positive
+// denominator (the quotient is that zero, sign included): most sites have no better neighbour, so the
+// neighbour-aware term's numerator kappa max(0, best) is an exact zero for them (spgg.py:489)
+// (the optimiser must not see that the replaced operand is only used where z is false - it would fold the
+// select away and divide the zero after all, which is what happened: hence the empty asm)
+__device__ __forceinline__ double opaque(double x) {
+  asm("" : "+d"(x));
+  return x;
+}
+__device__ __forceinline__ double ddiv_zero_safe(double num, double den) {
+  const bool z = (num == 0.0) && (den > 0.0);
+  const double q = __ddiv_rn(opaque(z ? 1.0 : num), den);
+  return z ? num : q;
+}
+
 // reputation state spgg.py:292-307: (sum over self + offsets of R)/n > 0, reference order
 template <class RT, int M>
 __device__ __forceinline__ int rep_state(const RT *smR, int sr, int sc) {
@@ -282,7 +297,13 @@ __device__ __forceinline__ int rep_state(const RT *smR, int sr, int sc) {
 #pragma unroll
     for (int k = 0; k < NK; ++k)
       acc = __dadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
-    return __ddiv_rn(acc, (double)(NK + 1)) > 0.0;
+    // sign of acc / n: that of acc, unless the quotient underflows (|acc| below 1e-300: divide).  The division
+    // always runs on a harmless operand: the compiler evaluates it for every lane, and a ZERO numerator - the
+    // common case while reputations are small integers - sends __ddiv_rn through its slow path (84
+    // instructions per call, profiles/r02_fp64_lean.md)
+    const bool plain = fabs(acc) > 1e-300 || acc == 0.0;
+    const double quot = __ddiv_rn(opaque(plain ? 1.0 : acc), (double)(NK + 1));
+    return plain ? (acc > 0.0) : (quot > 0.0);
   }
 }
 
@@ -575,7 +596,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
 template <class Md>
 struct SmemLayout {
   size_t off_code, off_val, off_R, off_C, off_N, off_tab, off_red, total;
-  __host__ __device__ explicit SmemLayout(int TR) {
+  __host__ __device__ constexpr explicit SmemLayout(int TR)
+      : off_code(0), off_val(0), off_R(0), off_C(0), off_N(0), off_tab(0), off_red(0), total(0) {
     const size_t n = (size_t)(TR + 2 * HR) * SMW;
     size_t o = 0;
     off_val = o;  o = (o + sizeof(typename Md::Val) * n + 15) / 16 * 16;
@@ -929,7 +951,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
               qtd = cq[e];
               const QT td2 = q_sub(q_add(vx, q_mul(g_, q_max(cq[r0i], cq[r0i + 1]))), qtd);
               QT lam;
-              if constexpr (Md::kFp64) lam = __ddiv_rn(__dmul_rn(rc.kappa, fmax(0.0, best)), den);
+              if constexpr (Md::kFp64) lam = ddiv_zero_safe(__dmul_rn(rc.kappa, fmax(0.0, best)), den);
               else lam = __fmul_rn(__fmul_rn(rc.kappa_f, fmaxf(0.0f, best)), inv_den);
               const QT nu = same ? lam : -lam;
               t1[e] = q_add(t1[e], nu);                      // spgg.py:499-505: both tables
@@ -968,7 +990,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
               const double mx = next_value(na, nb, ex1, rn1);
               const double td = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, mx)), qe);  // algorithms.py:128
               qtd = __dadd_rn(qe, __dmul_rn(rc.alpha, td));                              // algorithms.py:131
-              const double lam = __ddiv_rn(__dmul_rn(rc.kappa, fmax(0.0, best)), den);   // spgg.py:489
+              const double lam = ddiv_zero_safe(__dmul_rn(rc.kappa, fmax(0.0, best)), den);  // spgg.py:489
               const double nu = same ? lam : -lam;                                       // spgg.py:494-495
               // TD error on the table after the TD write (spgg.py:446-473)
               const double na2 = (s_new == s && act == 0) ? qtd : na;
@@ -977,7 +999,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
               qfin = __dadd_rn(qtd, nu);                                                 // spgg.py:509
               const double an = fabs(nu);
               sumNI += __dmul_rn(
-                  __ddiv_rn(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)),
+                  ddiv_zero_safe(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)),
                   100.0);                                                                // spgg.py:512
               // payoff / reward sums (spgg.py:381-392,419-426) come from exact integer counts at the fold,
               // as in the fp32 modes: sum P = ((rc SigmaN / 5 - 5 cost C n) - lo n) / span per class

@@ -15,9 +15,8 @@
 //   * the Q entries of the four sites a thread owns in a row (and their replayed draws) are loaded before
 //     the first of them is processed, and the Q rows of the CTA's next tile are prefetched into L2;
 //   * interior tiles store with plain stores (no ghost-copy tests per cell);
-//   * the divisions of the neighbour-aware term and of its statistic are skipped where the numerator is an
-//     exact zero (the quotient is that zero), which is most sites once domains have formed;
-//   * the reputation state compares the sum with zero instead of dividing it by the neighbourhood size.
+//   * no fp64 division ever sees an exactly-zero numerator (ddiv_zero_safe, rep_state): __ddiv_rn's slow path,
+//     84 instructions per call, was taken by two divisions of nearly every site.
 #pragma once
 #include "spgg_kernels.cuh"
 
@@ -47,30 +46,6 @@ __global__ void k_build_valtab(const RepConst *rc_all, double *tab) {
 
 template <bool B>
 struct BoolC { static constexpr bool value = B; };
-
-// sign of the neighbourhood mean (spgg.py:292-307) without the division: x / n > 0 <=> x > 0 unless the
-// quotient underflows, which needs |x| below 1e-300 - there the division is done
-template <class RT, int M>
-__device__ __forceinline__ int rep_state_lean(const RT *smR, int sr, int sc) {
-  constexpr int NK = (M == 2) ? 12 : 4;
-  if constexpr (sizeof(RT) == 1) {
-    return rep_state<RT, M>(smR, sr, sc);
-  } else if constexpr (sizeof(RT) == 4) {
-    float acc = smR[sr * SMW + sc];
-#pragma unroll
-    for (int k = 0; k < NK; ++k)
-      acc = __fadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
-    if (fabsf(acc) > 1e-30f) return acc > 0.0f;
-    return __fdiv_rn(acc, (float)(NK + 1)) > 0.0f;
-  } else {
-    double acc = smR[sr * SMW + sc];
-#pragma unroll
-    for (int k = 0; k < NK; ++k)
-      acc = __dadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
-    if (fabs(acc) > 1e-300) return acc > 0.0;
-    return __ddiv_rn(acc, (double)(NK + 1)) > 0.0;
-  }
-}
 
 // Stages the halo'd planes of a tile with every global load of a thread in flight at once (the general
 // kernel's element loops expose one memory round trip per element: ncu, profiles/r02_fp64_lean.md).
@@ -230,6 +205,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax_lean(GArgs a) {
   }
 }
 
+constexpr int LEAN_TR_MAX = 16;
+
 #ifndef SPGG_LEAN_MINBLOCKS
 #define SPGG_LEAN_MINBLOCKS 2
 #endif
@@ -252,7 +229,9 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
   const bool sel = (a.do_select != 0) && !(stop >= 0 && a.j == stop);
 
   extern __shared__ __align__(16) unsigned char smem[];
-  const SmemLayout<Md> lay(g.TR);
+  // the layout of the largest tile (16 rows) whatever g.TR is: the offsets are immediates instead of values
+  // the compiler recomputes inside the loop (spgg_create sizes the dynamic shared memory accordingly)
+  constexpr SmemLayout<Md> lay(LEAN_TR_MAX);
   Val *sm_val = reinterpret_cast<Val *>(smem + lay.off_val);
   RT *sm_R = reinterpret_cast<RT *>(smem + lay.off_R);
   Code *sm_code = reinterpret_cast<Code *>(smem + lay.off_code);
@@ -325,6 +304,13 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
         }
       }
     }
+    // ... and this warp's first row of this tile on its way into L1 while the tile is staged
+    auto prefetch_row_l1 = [&](int rr) {
+      constexpr int kLines = TC * 4 * (int)sizeof(QT) / 128;       // 128-byte lines of a 128-site row segment
+      if (lane < kLines && r0 + rr < g.rows && c0 + lane * (TC / kLines) < g.L)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(Qp + ((long long)(r0 + rr) * g.L + c0) * 4 + lane * (128 / (int)sizeof(QT))));
+    };
+    prefetch_row_l1(warp);
     // ---- stage the halo'd tiles: reward codes (+ their rewards), reputations, cooperator flags
     stage_tile<Md, M, true>(g, r0, c0, code_in, R_in, S_in, rc, sm_tab, vtab, sm_val, sm_code, sm_R, sm_C);
     __syncthreads();
@@ -356,6 +342,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
       constexpr bool INTERIOR = decltype(interiorc)::value;
       const int i = r0 + rr;
       const int sr = rr + HR;
+      if (rr + nw < g.TR) prefetch_row_l1(rr + nw);    // the warp's next row
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel && !REPLAY) {
         // counter = (column / 4, global row, iteration, 0), as in k_step
@@ -412,7 +399,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
           const RT r_old = sm_R[sidx];
           const int Ccur = sm_C[sidx];
           // post-action state of iteration j == pre-action state of iteration j+1 (spgg.py:409/423)
-          const int s_new = ACTION ? Ccur : rep_state_lean<RT, M>(sm_R, sr, sc);
+          const int s_new = ACTION ? Ccur : rep_state<RT, M>(sm_R, sr, sc);
           if constexpr (kI8) tri += (int)r_old;
           else if constexpr (sizeof(RT) == 4) trf += r_old;
           else sumR += r_old;
@@ -443,18 +430,15 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
             const double td = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, mx)), qe);     // algorithms.py:128
             const double qtd = __dadd_rn(qe, __dmul_rn(rc.alpha, td));                   // algorithms.py:131
             const double num = __dmul_rn(rc.kappa, fmax(0.0, best));
-            // an exact zero over a positive denominator is that zero: no division for the sites without a
-            // better neighbour
-            const double lam = (num == 0.0 && den > 0.0) ? num : __ddiv_rn(num, den);    // spgg.py:489
+            const double lam = ddiv_zero_safe(num, den);                                 // spgg.py:489
             const double nu = same ? lam : -lam;                                         // spgg.py:494-495
             const double na2 = (s_new == s && act == 0) ? qtd : na;
             const double nb2 = (s_new == s && act == 1) ? qtd : nb;
             const double td2 = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, fmax(na2, nb2))), qtd);
             qfin = __dadd_rn(qtd, nu);                                                   // spgg.py:509
             const double an = fabs(nu);
-            if (an != 0.0)                                                               // 0 / (x + 1e-8) * 100 adds +0
-              sumNI += __dmul_rn(
-                  __ddiv_rn(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)), 100.0);  // spgg.py:512
+            // 0 / (x + 1e-8) * 100 is +0: the same zero-numerator detour around __ddiv_rn's slow path
+            sumNI += __dmul_rn(ddiv_zero_safe(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)), 100.0);  // spgg.py:512
             pk_sn += (unsigned long long)sigma_n_of_code(code) << (16 * (wasC * 2 + coop));
             if (coop) sumRatio += rat[k4];
           } else {
