@@ -298,12 +298,16 @@ __device__ __forceinline__ int rep_state(const RT *smR, int sr, int sc) {
     for (int k = 0; k < NK; ++k)
       acc = __dadd_rn(acc, smR[(sr - c_off[k][0]) * SMW + (sc - c_off[k][1])]);
     // sign of acc / n: that of acc, unless the quotient underflows (|acc| below 1e-300: divide).  The division
-    // always runs on a harmless operand: the compiler evaluates it for every lane, and a ZERO numerator - the
-    // common case while reputations are small integers - sends __ddiv_rn through its slow path (84
-    // instructions per call, profiles/r02_fp64_lean.md)
+    // must stay inside its branch: evaluated for every lane (what the optimiser does with a pure expression) a
+    // ZERO numerator - the common case while reputations are small integers - sends __ddiv_rn through its
+    // slow path (84 instructions per call, profiles/r02_fp64_lean.md)
     const bool plain = fabs(acc) > 1e-300 || acc == 0.0;
-    const double quot = __ddiv_rn(opaque(plain ? 1.0 : acc), (double)(NK + 1));
-    return plain ? (acc > 0.0) : (quot > 0.0);
+    int st = acc > 0.0;
+    if (!plain) {
+      asm volatile("");   // not to be speculated: see above
+      st = __ddiv_rn(acc, (double)(NK + 1)) > 0.0;
+    }
+    return st;
   }
 }
 

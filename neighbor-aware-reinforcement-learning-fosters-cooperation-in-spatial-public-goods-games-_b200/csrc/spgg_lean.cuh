@@ -430,15 +430,23 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
             const double td = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, mx)), qe);     // algorithms.py:128
             const double qtd = __dadd_rn(qe, __dmul_rn(rc.alpha, td));                   // algorithms.py:131
             const double num = __dmul_rn(rc.kappa, fmax(0.0, best));
-            const double lam = ddiv_zero_safe(num, den);                                 // spgg.py:489
-            const double nu = same ? lam : -lam;                                         // spgg.py:494-495
             const double na2 = (s_new == s && act == 0) ? qtd : na;
             const double nb2 = (s_new == s && act == 1) ? qtd : nb;
             const double td2 = __dsub_rn(__dadd_rn(vx, __dmul_rn(rc.gamma, fmax(na2, nb2))), qtd);
+            // A site without a better neighbour has an exactly-zero numerator: lambda is that zero and the NI
+            // statistic adds +0.  Both divisions of the other sites sit in ONE block the optimiser cannot
+            // speculate (the empty volatile asm): a division it evaluates for every lane sends the zero
+            // numerators through __ddiv_rn's slow path, 84 instructions per call (profiles/r02_fp64_lean.md);
+            // once domains have formed whole warps skip the block.
+            double lam = num;                                                            // spgg.py:489
+            if (!(num == 0.0 && den > 0.0)) {
+              asm volatile("");
+              lam = __ddiv_rn(num, den);
+              const double an = fabs(lam);
+              sumNI += __dmul_rn(ddiv_zero_safe(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)), 100.0);  // spgg.py:512
+            }
+            const double nu = same ? lam : -lam;                                         // spgg.py:494-495
             qfin = __dadd_rn(qtd, nu);                                                   // spgg.py:509
-            const double an = fabs(nu);
-            // 0 / (x + 1e-8) * 100 is +0: the same zero-numerator detour around __ddiv_rn's slow path
-            sumNI += __dmul_rn(ddiv_zero_safe(an, __dadd_rn(__dadd_rn(fabs(__dmul_rn(rc.alpha, td2)), an), 1e-8)), 100.0);  // spgg.py:512
             pk_sn += (unsigned long long)sigma_n_of_code(code) << (16 * (wasC * 2 + coop));
             if (coop) sumRatio += rat[k4];
           } else {
