@@ -114,9 +114,11 @@ def c4_config(L, inner):
 def c5_config(L, world, inner):
     """`config` of the N > 1 line (both arms print the same one)."""
     return {"workload": f"C5: one L={L} lattice in {world} row strips, reputation state, M=1, r=3, kappa=1, "
-                        f"w_P=0.95, Q-learning; {inner} iterations per bench step, per iteration one halo "
-                        "exchange (NCCL send/recv) and one 4-float all-reduce(MAX) of the strips' reports "
-                        "(global reward-difference maximum, uniform-lattice test); statistics on, Philox draws",
+                        f"w_P=0.95, Q-learning; {inner} iterations per bench step, per iteration the two boundary "
+                        "rows of every strip reach its neighbours' ghost rows and the strips' 4-float reports (global "
+                        "reward-difference maximum, uniform-lattice test) are max-combined - through peer-mapped memory "
+                        "over NVLink where the planes can be mapped, NCCL send/recv + all-reduce otherwise "
+                        "(extras.transport of the native line says which); statistics on, Philox draws",
             "L": L, "iterations_per_step": inner, "n_strips": world,
             "precision": "fp32 Q (float4) + int8 R + bit S",
             "l2": "per-GPU state far larger than the 126 MB L2 (no flush needed)",

@@ -65,6 +65,7 @@ __device__ __forceinline__ void stage_tile(const Geom &g, int r0, int c0, const 
   typedef typename Md::Val Val;
   constexpr int NQ = (TC + 4 + 31) / 32, MAXIT = 3;   // (TR + 4) rows / nw warps <= 3 for every geometry spgg_create picks
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((g.TR + 4 + nw - 1) / nw > MAXIT) __trap();      // a geometry this staging does not cover must not run silently
   const int cmax = g.L + GC;                       // first column without a current image
   // strategy words can be taken whole where no column of the halo'd tile wraps
   const bool wordpath = STEP && c0 >= 32 && c0 + TC + 2 <= g.L;

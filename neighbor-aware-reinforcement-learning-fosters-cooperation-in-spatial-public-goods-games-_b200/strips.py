@@ -464,6 +464,8 @@ def bench_main(args, rank: int, local_rank: int, world: int):
     se.sync()
     launches = se.kernel_launches() - l0
     reruns_timed = se.reruns
+    transport = {"halo": "peer-mapped planes (stores over NVLink)" if se.p2p else "NCCL send/recv",
+                 "reports": "peer-mapped rings (system-scope atomics)" if se.ring else "NCCL all-reduce(MAX)"}
     spec = se.eng.status()
     n_sites = L * L
     value = n_sites * inner * K / (ms * 1e-3)
@@ -575,6 +577,7 @@ def bench_main(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": None,
             "parity_check": parity,
             "extras": {"strip_rows": strip_rows_n, "us_per_iteration": 1e3 * ms / (K * inner),
+                       "transport": transport,
                        "compute_only_us_per_iteration": solo_us,
                        "communication_not_hidden_frac": 1.0 - solo_us / (1e3 * ms / (K * inner)),
                        "speculation": {"launches": int(spec.speculative_launches), "reruns_in_timed_region": int(reruns_timed)},
