@@ -596,6 +596,87 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax(GArgs a) {
 }
 
 
+// Stages the halo'd planes of a tile with every global load of a thread in flight at once (the general
+// kernel's element loops expose one memory round trip per element: ncu, profiles/r02_fp64_lean.md).
+// A warp owns the staged rows r = warp, warp + nw, warp + 2 nw of rows -2 .. TR+1:
+//   phase A  raw loads: reward codes and reputations (halo M; ghost columns and ghost rows of the planes hold
+//            the periodic images, store_cell keeps GC >= M of them current) and the six strategy words of a row
+//   phase B  stores of codes / reputations / cooperator flags, and the reward-table lookups (fp64) of all rows
+//   phase C  reward stores
+// STEP = false stages the rewards only (k_gmax_lean).
+template <class Md, int M, bool STEP>
+__device__ __forceinline__ void stage_tile(const Geom &g, int r0, int c0, const typename Md::Code *code_in,
+                                           const typename Md::R *R_in, const uint32_t *S_in, const RepConst &rc,
+                                           const float *sm_tab, const double *vtab, typename Md::Val *sm_val,
+                                           typename Md::Code *sm_code, typename Md::R *sm_R, uint8_t *sm_C) {
+  typedef typename Md::Code Code;
+  typedef typename Md::R RT;
+  typedef typename Md::Val Val;
+  constexpr int NQ = (TC + 4 + 31) / 32, MAXIT = 3;   // (TR + 4) rows / nw warps <= 3 for every geometry spgg_create picks
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((g.TR + 4 + nw - 1) / nw > MAXIT) __trap();      // a geometry this staging does not cover must not run silently
+  const int cmax = g.L + GC;                       // first column without a current image
+  // strategy words can be taken whole where no column of the halo'd tile wraps
+  const bool wordpath = STEP && c0 >= 32 && c0 + TC + 2 <= g.L;
+  Code cv[MAXIT][NQ];
+  RT rv[MAXIT][NQ];
+  uint32_t sw[MAXIT];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int r = warp + it * nw, rr = r - 2, prow = r0 + rr + GH;
+    const bool rowok = r < g.TR + 4 && prow < g.rows + 2 * GH;
+    const bool in_cr = rowok && rr >= -M && rr < g.TR + M;
+    const long long rowoff = (long long)prow * g.pitchB + CPAD + c0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int cc = q * 32 + lane - 2;
+      const bool ok = in_cr && cc >= -M && cc < TC + M && c0 + cc < cmax;
+      cv[it][q] = ok ? code_in[rowoff + cc] : Code(0);
+      if constexpr (STEP) rv[it][q] = ok ? R_in[rowoff + cc] : RT(0);
+    }
+    if constexpr (STEP)
+      sw[it] = (wordpath && rowok && lane < 6) ? S_in[(long long)prow * g.pitchW + WPAD + (c0 >> 5) - 1 + lane] : 0u;
+  }
+  Val vv[MAXIT][NQ];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int r = warp + it * nw, rr = r - 2;
+    const bool rowact = r < g.TR + 4;
+    const bool in_cr = rowact && rr >= -M && rr < g.TR + M;
+    const int base = (rr + HR) * SMW + HP;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int cc = q * 32 + lane - 2;
+      if constexpr (Md::kFp64) vv[it][q] = __ldg(vtab + 2 * (size_t)(cv[it][q] >> 1));   // code 0 is a valid entry
+      else vv[it][q] = sm_tab[cv[it][q] >> 1];
+      if constexpr (STEP) {
+        if (in_cr && cc >= -M && cc < TC + M) {
+          sm_code[base + cc] = cv[it][q];
+          sm_R[base + cc] = rv[it][q];
+        }
+        // cooperator flag of the cell: bit cc & 31 of word (cc + 32) >> 5 of the six (c0 is a multiple of 32)
+        const uint32_t w = __shfl_sync(0xffffffffu, sw[it], (cc + 32) >> 5);
+        const bool rowok = r0 + rr + GH < g.rows + 2 * GH;      // rows below the ghost rows read as defectors
+        if (wordpath && rowact && cc < TC + 2) sm_C[base + cc] = rowok ? (uint8_t)((~w >> (cc & 31)) & 1u) : (uint8_t)0;
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int r = warp + it * nw, rr = r - 2;
+    const bool in_cr = r < g.TR + 4 && rr >= -M && rr < g.TR + M;
+    const int base = (rr + HR) * SMW + HP;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int cc = q * 32 + lane - 2;
+      if (in_cr && cc >= -M && cc < TC + M) sm_val[base + cc] = vv[it][q];
+    }
+  }
+  if constexpr (STEP) {
+    if (!wordpath) load_coop_tile(sm_C, S_in, g, r0, c0, g.TR);   // edge tile columns: per-cell wrap
+  }
+}
+
 // =================================================================== k_step
 template <class Md>
 struct SmemLayout {
@@ -798,28 +879,24 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_GEN_MINBLOCKS) k_step(KArgs 
   for (int tile = cta; tile < n_tiles; tile += g.ctas_per_rep) {
     const int r0 = (tile / g.n_tx) * g.TR, c0 = (tile % g.n_tx) * TC;
     __syncthreads();
-    // ---- stage tiles + halos
-    if (upd) load_tile<Code, M>(sm_code, code_in, g, r0, c0, g.TR);
-    load_tile<RT, ACTION ? 0 : M>(sm_R, R_in, g, r0, c0, g.TR);
-    load_coop_tile(sm_C, S_in, g, r0, c0, g.TR);
+    // ---- stage tiles + halos: all loads of a thread in flight at once (stage_tile; the codes and their rewards are
+    // staged for a select-only launch too - they are not read then)
+    stage_tile<Md, M, true>(g, r0, c0, code_in, R_in, S_in, rc, sm_tab, vtab, sm_val, sm_code, sm_R, sm_C);
     __syncthreads();
-    if (upd) {
-      constexpr int NC = TC + 2 * M;
-      const int nr = g.TR + 2 * M;
-      for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
-        const int idx = (e / NC - M + HR) * SMW + (e % NC - M + HP);
-        sm_val[idx] = val_of_code<Md>(sm_code[idx], rc, sm_tab, vtab);
-      }
-    }
     {
       // N = cooperators in the 5-site group centred on each site (spgg.py:23-36) of S_j,
       // for the tile and a one-site ring
-      constexpr int NC = TC + 2;
       const int nr = g.TR + 2;
-      for (int e = threadIdx.x; e < nr * NC; e += blockDim.x) {
-        const int idx = (e / NC - 1 + HR) * SMW + (e % NC - 1 + HP);
-        sm_N[idx] = (uint8_t)(sm_C[idx] + sm_C[idx + SMW] + sm_C[idx - SMW] + sm_C[idx + 1] +
-                              sm_C[idx - 1]);
+      for (int r = warp; r < nr; r += nw) {
+        const int base = (r - 1 + HR) * SMW + HP;
+#pragma unroll
+        for (int q = 0; q < (TC + 2 + 31) / 32; ++q) {
+          const int cc = q * 32 + lane - 1;
+          if (cc < TC + 1) {
+            const int idx = base + cc;
+            sm_N[idx] = (uint8_t)(sm_C[idx] + sm_C[idx + SMW] + sm_C[idx - SMW] + sm_C[idx + 1] + sm_C[idx - 1]);
+          }
+        }
       }
     }
     __syncthreads();

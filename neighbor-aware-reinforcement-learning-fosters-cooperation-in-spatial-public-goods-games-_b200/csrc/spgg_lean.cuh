@@ -10,8 +10,9 @@
 //   * Q-learning and "update" are compile-time facts (the host launches it for algo 0, do_update = 1);
 //   * the reward of an fp64 code is a table lookup (KArgs::valtab, built once per handle by k_build_valtab
 //     with payoff_f64 / reward_f64 themselves) instead of an fp64 division per staged site;
-//   * tiles are staged row by row (a warp per staged row, no division per element), the code -> reward pass
-//     is fused into the code load, ghost columns are read instead of wrapped;
+//   * tiles are staged with every global load of a thread in flight at once (stage_tile in spgg_kernels.cuh,
+//     shared with k_step): no division per element, the code -> reward pass fused into the code load, ghost
+//     columns read instead of wrapped;
 //   * the Q entries of the four sites a thread owns in a row (and their replayed draws) are loaded before
 //     the first of them is processed, and the Q rows of the CTA's next tile are prefetched into L2;
 //   * interior tiles store with plain stores (no ghost-copy tests per cell);
@@ -46,87 +47,6 @@ __global__ void k_build_valtab(const RepConst *rc_all, double *tab) {
 
 template <bool B>
 struct BoolC { static constexpr bool value = B; };
-
-// Stages the halo'd planes of a tile with every global load of a thread in flight at once (the general
-// kernel's element loops expose one memory round trip per element: ncu, profiles/r02_fp64_lean.md).
-// A warp owns the staged rows r = warp, warp + nw, warp + 2 nw of rows -2 .. TR+1:
-//   phase A  raw loads: reward codes and reputations (halo M; ghost columns and ghost rows of the planes hold
-//            the periodic images, store_cell keeps GC >= M of them current) and the six strategy words of a row
-//   phase B  stores of codes / reputations / cooperator flags, and the reward-table lookups (fp64) of all rows
-//   phase C  reward stores
-// STEP = false stages the rewards only (k_gmax_lean).
-template <class Md, int M, bool STEP>
-__device__ __forceinline__ void stage_tile(const Geom &g, int r0, int c0, const typename Md::Code *code_in,
-                                           const typename Md::R *R_in, const uint32_t *S_in, const RepConst &rc,
-                                           const float *sm_tab, const double *vtab, typename Md::Val *sm_val,
-                                           typename Md::Code *sm_code, typename Md::R *sm_R, uint8_t *sm_C) {
-  typedef typename Md::Code Code;
-  typedef typename Md::R RT;
-  typedef typename Md::Val Val;
-  constexpr int NQ = (TC + 4 + 31) / 32, MAXIT = 3;   // (TR + 4) rows / nw warps <= 3 for every geometry spgg_create picks
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if ((g.TR + 4 + nw - 1) / nw > MAXIT) __trap();      // a geometry this staging does not cover must not run silently
-  const int cmax = g.L + GC;                       // first column without a current image
-  // strategy words can be taken whole where no column of the halo'd tile wraps
-  const bool wordpath = STEP && c0 >= 32 && c0 + TC + 2 <= g.L;
-  Code cv[MAXIT][NQ];
-  RT rv[MAXIT][NQ];
-  uint32_t sw[MAXIT];
-#pragma unroll
-  for (int it = 0; it < MAXIT; ++it) {
-    const int r = warp + it * nw, rr = r - 2, prow = r0 + rr + GH;
-    const bool rowok = r < g.TR + 4 && prow < g.rows + 2 * GH;
-    const bool in_cr = rowok && rr >= -M && rr < g.TR + M;
-    const long long rowoff = (long long)prow * g.pitchB + CPAD + c0;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int cc = q * 32 + lane - 2;
-      const bool ok = in_cr && cc >= -M && cc < TC + M && c0 + cc < cmax;
-      cv[it][q] = ok ? code_in[rowoff + cc] : Code(0);
-      if constexpr (STEP) rv[it][q] = ok ? R_in[rowoff + cc] : RT(0);
-    }
-    if constexpr (STEP)
-      sw[it] = (wordpath && rowok && lane < 6) ? S_in[(long long)prow * g.pitchW + WPAD + (c0 >> 5) - 1 + lane] : 0u;
-  }
-  Val vv[MAXIT][NQ];
-#pragma unroll
-  for (int it = 0; it < MAXIT; ++it) {
-    const int r = warp + it * nw, rr = r - 2;
-    const bool rowact = r < g.TR + 4;
-    const bool in_cr = rowact && rr >= -M && rr < g.TR + M;
-    const int base = (rr + HR) * SMW + HP;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int cc = q * 32 + lane - 2;
-      if constexpr (Md::kFp64) vv[it][q] = __ldg(vtab + 2 * (size_t)(cv[it][q] >> 1));   // code 0 is a valid entry
-      else vv[it][q] = sm_tab[cv[it][q] >> 1];
-      if constexpr (STEP) {
-        if (in_cr && cc >= -M && cc < TC + M) {
-          sm_code[base + cc] = cv[it][q];
-          sm_R[base + cc] = rv[it][q];
-        }
-        // cooperator flag of the cell: bit cc & 31 of word (cc + 32) >> 5 of the six (c0 is a multiple of 32)
-        const uint32_t w = __shfl_sync(0xffffffffu, sw[it], (cc + 32) >> 5);
-        const bool rowok = r0 + rr + GH < g.rows + 2 * GH;      // rows below the ghost rows read as defectors
-        if (wordpath && rowact && cc < TC + 2) sm_C[base + cc] = rowok ? (uint8_t)((~w >> (cc & 31)) & 1u) : (uint8_t)0;
-      }
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < MAXIT; ++it) {
-    const int r = warp + it * nw, rr = r - 2;
-    const bool in_cr = r < g.TR + 4 && rr >= -M && rr < g.TR + M;
-    const int base = (rr + HR) * SMW + HP;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int cc = q * 32 + lane - 2;
-      if (in_cr && cc >= -M && cc < TC + M) sm_val[base + cc] = vv[it][q];
-    }
-  }
-  if constexpr (STEP) {
-    if (!wordpath) load_coop_tile(sm_C, S_in, g, r0, c0, g.TR);   // edge tile columns: per-cell wrap
-  }
-}
 
 // Lattice-global max |reward difference| over neighbour pairs (spgg.py:486-488), lean version of k_gmax:
 // tiles staged row by row with the rewards looked up while they land, and every unordered pair taken once
