@@ -3,8 +3,8 @@
 // computes needs a CUDA device and fails with SPGG_E_CUDA otherwise.
 #include "../../include/spgg.h"
 #include "spgg_kernels.cuh"
+#include "spgg_dispatch.h"
 #include "spgg_fast.cuh"
-#include "spgg_lean.cuh"
 #include "spgg_resident.cuh"
 
 #include <cudaTypedefs.h>
@@ -40,7 +40,6 @@ static int fail(int code, const char *fmt, ...) {
                   __FILE__, __LINE__);                                                  \
   } while (0)
 
-enum { MODE_F32_I8 = 0, MODE_F32_F = 1, MODE_F64 = 2 };
 
 struct spgg_handle {
   int device = 0;
@@ -194,55 +193,9 @@ static void build_repconst(const spgg_params_t &p, RepConst *rc) {
 }
 
 // ---------------------------------------------------------------- dispatch
-typedef void (*step_fn_t)(KArgs);
-typedef void (*gmax_fn_t)(GArgs);
-
-template <class Md, int M>
-static step_fn_t pick_step2(int action, int replay) {
-  if (action) return replay ? k_step<Md, M, true, true> : k_step<Md, M, true, false>;
-  return replay ? k_step<Md, M, false, true> : k_step<Md, M, false, false>;
-}
-template <class Md>
-static step_fn_t pick_step1(int M, int action, int replay) {
-  return M == 2 ? pick_step2<Md, 2>(action, replay) : pick_step2<Md, 1>(action, replay);
-}
-static step_fn_t pick_step(int mode, int M, int action, int replay) {
-  switch (mode) {
-    case MODE_F32_I8: return pick_step1<ModeF32I8>(M, action, replay);
-    case MODE_F32_F: return pick_step1<ModeF32F>(M, action, replay);
-    default: return pick_step1<ModeF64>(M, action, replay);
-  }
-}
-template <class Md, int M>
-static step_fn_t pick_lean2(int action, int replay) {
-  if (action) return replay ? k_step_lean<Md, M, true, true> : k_step_lean<Md, M, true, false>;
-  return replay ? k_step_lean<Md, M, false, true> : k_step_lean<Md, M, false, false>;
-}
-template <class Md>
-static step_fn_t pick_lean1(int M, int action, int replay) {
-  return M == 2 ? pick_lean2<Md, 2>(action, replay) : pick_lean2<Md, 1>(action, replay);
-}
-// the lean Q-learning update of the general path (spgg_lean.cuh)
-static step_fn_t pick_lean(int mode, int M, int action, int replay) {
-  switch (mode) {
-    case MODE_F32_I8: return pick_lean1<ModeF32I8>(M, action, replay);
-    case MODE_F32_F: return pick_lean1<ModeF32F>(M, action, replay);
-    default: return pick_lean1<ModeF64>(M, action, replay);
-  }
-}
+// the general and the lean kernels are instantiated in their own translation units (spgg_dispatch.h)
 static gmax_fn_t pick_gmax(int mode, int M, bool lean) {
-  if (lean) {   // k_gmax_lean: same value, every pair once
-    switch (mode) {
-      case MODE_F32_I8: return M == 2 ? k_gmax_lean<ModeF32I8, 2> : k_gmax_lean<ModeF32I8, 1>;
-      case MODE_F32_F: return M == 2 ? k_gmax_lean<ModeF32F, 2> : k_gmax_lean<ModeF32F, 1>;
-      default: return M == 2 ? k_gmax_lean<ModeF64, 2> : k_gmax_lean<ModeF64, 1>;
-    }
-  }
-  switch (mode) {
-    case MODE_F32_I8: return M == 2 ? k_gmax<ModeF32I8, 2> : k_gmax<ModeF32I8, 1>;
-    case MODE_F32_F: return M == 2 ? k_gmax<ModeF32F, 2> : k_gmax<ModeF32F, 1>;
-    default: return M == 2 ? k_gmax<ModeF64, 2> : k_gmax<ModeF64, 1>;
-  }
+  return lean ? pick_gmax_lean(mode, M) : pick_gmax_general(mode, M);
 }
 static size_t step_smem(int mode, int TR) {
   switch (mode) {
@@ -630,8 +583,7 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
       free_all(h); delete h;
       return fail(SPGG_E_CUDA, "cudaMalloc(%zu bytes) failed (reward table)", vb);
     }
-    k_build_valtab<<<dim3((1u << VALTAB_BITS) / 256, (unsigned)n_replicas), 256>>>(h->d_rc, h->d_valtab);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_build_valtab(h->d_rc, h->d_valtab, n_replicas));
   }
   std::vector<int> neg(n_replicas, -1);
   CUDA_TRY(cudaMemcpy(h->d_stop, neg.data(), sizeof(int) * n_replicas, cudaMemcpyHostToDevice));

@@ -1434,7 +1434,7 @@ __global__ void k_state_digest(Geom g, int rep, const void *Qd, const void *Rd, 
 }
 
 // Strips: the per-iteration vector {max, any D, any C, -} has been max-reduced over the ranks.  One thread.
-__global__ void k_strip_verify(float *gvec, int rel, int j, int was_upd, int was_spec, int was_sel, float *gcarry,
+static __global__ void k_strip_verify(float *gvec, int rel, int j, int was_upd, int was_spec, int was_sel, float *gcarry,
                                float *gmax_tab, int *bad_at, int *stop_at) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (*bad_at < rel) return;                        // a failed guess earlier in the chunk: nothing after it ran
@@ -1487,7 +1487,7 @@ __global__ void k_r_histogram(Geom g, int rep, const void *Rd, double rq, int nb
 
 // Strips, ring mode: wait until every rank has combined its report of launch `gen` into this rank's ring slot,
 // publish it as gvec[rel] and take the verdict (k_strip_verify's logic).  One thread; spins on its own memory.
-__global__ void k_ring_verify(unsigned *ring, int gen, int world, float *gvec, int rel, int j, int was_upd, int was_spec,
+static __global__ void k_ring_verify(unsigned *ring, int gen, int world, float *gvec, int rel, int j, int was_upd, int was_spec,
                               int was_sel, float *gcarry, float *gmax_tab, int *bad_at, int *stop_at) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (*bad_at < rel) return;                        // nothing after a failed guess ran - and nothing was pushed

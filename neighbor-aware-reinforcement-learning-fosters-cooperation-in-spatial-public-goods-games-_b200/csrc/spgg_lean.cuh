@@ -19,6 +19,7 @@
 //   * no fp64 division ever sees an exactly-zero numerator (ddiv_zero_safe, rep_state): __ddiv_rn's slow path,
 //     84 instructions per call, was taken by two divisions of nearly every site.
 #pragma once
+#include "spgg_dispatch.h"
 #include "spgg_kernels.cuh"
 
 namespace spgg {
@@ -125,8 +126,6 @@ __global__ void __launch_bounds__(MAX_THREADS) k_gmax_lean(GArgs a) {
       atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(m));
   }
 }
-
-constexpr int LEAN_TR_MAX = 16;
 
 #ifndef SPGG_LEAN_MINBLOCKS
 #define SPGG_LEAN_MINBLOCKS 2
