@@ -121,3 +121,45 @@ def test_lean_batched_replicas_and_early_exit(monkeypatch):
     assert res[0][:2] == res[1][:2] == (1, 1)
     for x, y in zip(res[0][2:], res[1][2:]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("path,L", [("general", 24), ("fast", 128)])
+def test_stopped_replica_keeps_its_state_across_chunks(monkeypatch, path, L):
+    """A replica of a batch that stopped (spgg.py:405) in an earlier chunk is not touched by the launches of
+    the later ones: its planes - and, on the fast path, its half of the Q ping-pong pair - must be carried to
+    whatever parity the running replicas end on (finish_pending in spgg_capi.cu)."""
+    monkeypatch.setenv("SPGG_NO_RESIDENT", "1")
+    if path == "general":
+        monkeypatch.setenv("SPGG_NO_FAST", "1")
+    else:
+        monkeypatch.delenv("SPGG_NO_FAST", raising=False)
+    monkeypatch.delenv("SPGG_NO_LEAN", raising=False)
+    p_stop = full_params(dict(C1, L=L, epsilon=0.0, epsilon_min=0.0))
+    p_run = full_params(dict(C1, L=L))
+    rs = np.random.RandomState(4)
+    Q0 = np.zeros((L, L, 2, 2))
+    Q0[..., 1] = 1.0                      # everybody prefers to defect: uniform after iteration 1
+    S0 = rs.randint(0, 2, (L, L))
+    S1 = rs.randint(0, 2, (L, L))
+    Q1 = rs.uniform(-0.01, 0.01, (L, L, 2, 2)).astype(np.float32).astype(np.float64)
+    eng = _engine([p_stop, p_run], seeds=[1, 2], precision="fp32")
+    assert path in eng.describe()
+    eng.set_state(S0, np.zeros((L, L)), Q0, replica=0)
+    eng.set_state(S1, np.zeros((L, L)), Q1, replica=1)
+    eng.step(10)
+    assert eng.status(0).stopped_at == 1 and eng.status(1).iteration == 10
+    first = eng.get_state(0)
+    for n in (5, 4, 1, 6):                 # odd and even chunk lengths: every parity combination
+        eng.step(n)
+        assert eng.status(0).iteration == 1
+        for x, y in zip(first, eng.get_state(0)):
+            assert np.array_equal(x, y)
+    assert eng.status(1).iteration == 26
+    # the running replica is what it would have been alone
+    solo = _engine(p_run, seeds=2, precision="fp32")
+    solo.set_state(S1, np.zeros((L, L)), Q1)
+    solo.step(26)
+    for x, y in zip(solo.get_state(), eng.get_state(1)):
+        assert np.array_equal(x, y)
+    solo.close()
+    eng.close()
