@@ -476,6 +476,10 @@ extern "C" int spgg_create(const spgg_params_t *params, int n_replicas, int devi
   }
   g.TR = h->fast ? FTR : (g.rows >= 512 ? 16 : (g.rows >= 64 ? 8 : 4));
   h->threads = h->fast ? FTHREADS : 32 * std::min(8, g.TR);
+  if (!h->fast && getenv("SPGG_GEN_TR") && getenv("SPGG_GEN_THREADS")) {   // tuning experiments: tile rows / block size of the general path
+    g.TR = std::max(4, std::min(16, atoi(getenv("SPGG_GEN_TR"))));
+    h->threads = std::max(32, std::min(256, atoi(getenv("SPGG_GEN_THREADS")) / 32 * 32));
+  }
   g.n_tx = (g.L + TC - 1) / TC;
   g.n_ty = (g.rows + g.TR - 1) / g.TR;
   g.n_rep = n_replicas;

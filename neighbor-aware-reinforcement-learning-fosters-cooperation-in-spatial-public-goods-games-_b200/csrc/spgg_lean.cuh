@@ -13,8 +13,8 @@
 //   * tiles are staged with every global load of a thread in flight at once (stage_tile in spgg_kernels.cuh,
 //     shared with k_step): no division per element, the code -> reward pass fused into the code load, ghost
 //     columns read instead of wrapped;
-//   * the Q entries of the four sites a thread owns in a row (and their replayed draws) are loaded before
-//     the first of them is processed, and the Q rows of the CTA's next tile are prefetched into L2;
+//   * the Q entries of a pair of the four sites a thread owns in a row (and their replayed draws) are loaded
+//     before the first of them is processed, and the Q rows of the CTA's next tile are prefetched into L2;
 //   * interior tiles store with plain stores (no ghost-copy tests per cell);
 //   * no fp64 division ever sees an exactly-zero numerator (ddiv_zero_safe, rep_state): __ddiv_rn's slow path,
 //     84 instructions per call, was taken by two divisions of nearly every site.
@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
       if (lane < kLines && r0 + rr < g.rows && c0 + lane * (TC / kLines) < g.L)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(Qp + ((long long)(r0 + rr) * g.L + c0) * 4 + lane * (128 / (int)sizeof(QT))));
     };
+#ifdef SPGG_LEAN_L1PF   // measured: 648 us per iteration with the L1 prefetches, 614 without (fp64, L=4096) - off
     prefetch_row_l1(warp);
+#endif
     // ---- stage the halo'd tiles: reward codes (+ their rewards), reputations, cooperator flags
     stage_tile<Md, M, true>(g, r0, c0, code_in, R_in, S_in, rc, sm_tab, vtab, sm_val, sm_code, sm_R, sm_C);
     __syncthreads();
@@ -262,7 +264,9 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
       constexpr bool INTERIOR = decltype(interiorc)::value;
       const int i = r0 + rr;
       const int sr = rr + HR;
+#ifdef SPGG_LEAN_L1PF
       if (rr + nw < g.TR) prefetch_row_l1(rr + nw);    // the warp's next row
+#endif
       uint32_t w4[4] = {0, 0, 0, 0};
       if (sel && !REPLAY) {
         // counter = (column / 4, global row, iteration, 0), as in k_step
@@ -277,14 +281,20 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
           w4[k4] = sel4<uint32_t>(lane & 3, x0, x1, x2, x3);
         }
       }
-      // ---- everything that comes from global memory for the four sites, before the first is processed
+      // ---- everything that comes from global memory for a batch of sites, before the first is processed
+// (measured at L=4096 in fp64: batches of 4 sites 648 us per iteration, pairs 630)
+#ifndef SPGG_LEAN_BATCH
+#define SPGG_LEAN_BATCH 2
+#endif
+#pragma unroll
+      for (int kb = 0; kb < 4; kb += SPGG_LEAN_BATCH) {
       QT q[4][4];
       double ru[4] = {0, 0, 0, 0};
       uint8_t rb[4] = {0, 0, 0, 0};
       double rat[4] = {0, 0, 0, 0};   // fp64: ratio statistic of the site's code (second table column)
       const long long site_row = (long long)i * g.L + c0 + lane;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
+      for (int k4 = kb; k4 < kb + SPGG_LEAN_BATCH; ++k4) {
         const bool valid = FULL || (c0 + 32 * k4 + lane < g.L);
         const long long site = site_row + 32 * k4;
         if (valid) {
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
         }
       }
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
+      for (int k4 = kb; k4 < kb + SPGG_LEAN_BATCH; ++k4) {
         const int cc = k4 * 32 + lane;
         const int col = c0 + cc;
         const bool valid = FULL || (col < g.L);
@@ -454,6 +464,7 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
           }
         }
       }
+      }   // batch
     };
 
     if (interior) {
