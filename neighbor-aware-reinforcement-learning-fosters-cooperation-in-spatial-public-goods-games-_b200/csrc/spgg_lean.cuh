@@ -224,13 +224,13 @@ __global__ void __launch_bounds__(MAX_THREADS, SPGG_LEAN_MINBLOCKS) k_step_lean(
         }
       }
     }
+#ifdef SPGG_LEAN_L1PF   // measured: 648 us per iteration with the L1 prefetches, 614 without (fp64, L=4096) - off
     // ... and this warp's first row of this tile on its way into L1 while the tile is staged
     auto prefetch_row_l1 = [&](int rr) {
       constexpr int kLines = TC * 4 * (int)sizeof(QT) / 128;       // 128-byte lines of a 128-site row segment
       if (lane < kLines && r0 + rr < g.rows && c0 + lane * (TC / kLines) < g.L)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(Qp + ((long long)(r0 + rr) * g.L + c0) * 4 + lane * (128 / (int)sizeof(QT))));
     };
-#ifdef SPGG_LEAN_L1PF   // measured: 648 us per iteration with the L1 prefetches, 614 without (fp64, L=4096) - off
     prefetch_row_l1(warp);
 #endif
     // ---- stage the halo'd tiles: reward codes (+ their rewards), reputations, cooperator flags
