@@ -261,3 +261,25 @@ def test_numpy_oracle_double_q_reproduces_reference(golden_dir, name):
     assert np.array_equal(out["q_final"], z["q_final"])
     for key in ("coop_rate_history", "switch_C_to_D", "neighbor_influence_percent", "avg_q_s0_c_history"):
         assert np.array_equal(out[key], z["ds_" + key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("r,cost,L", [(3.0, 1.0, 64), (3.6, 1.0, 37), (1.0, 0.5, 50), (5.0, 1.0, 20)])
+def test_payoff_sums_from_integer_counts(r, cost, L):
+    """The kernels' statistics row takes the payoff sums per class (spgg.py:381-392) from exact integer
+    counts - sum of P over a class = ((r c SigmaN / 5 - 5 cost C n) - lo n) / span, SigmaN the cooperators
+    summed over the five groups of a site (csrc/spgg_kernels.cuh: step_epilogue) - instead of summing the
+    per-site payoffs of spgg.py:373-377.  The two agree to rounding (the series are compared to 1e-9)."""
+    from oracle import spgg_numpy as sn
+    rs = np.random.RandomState(int(r * 10) + L)
+    for frac in (0.5, 0.05, 0.95):
+        S = (rs.rand(L, L) < frac).astype(np.int64)             # 1 = defector
+        P = sn.normalised_payoff(S, r, 1, cost)
+        C = (S == 0).astype(np.int64)
+        N = sn.group_counts(C)
+        sigma = sum(sn.at(N, di, dj) for (di, dj) in ((0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)))
+        lo, span = r - 5, 4 * r - (r - 5)
+        for cls, mask in (("C", C == 1), ("D", C == 0)):
+            n = int(mask.sum())
+            direct = float(P[mask].sum())
+            from_counts = ((r * 1 * float(sigma[mask].sum()) / 5.0 - 5.0 * cost * (cls == "C") * n) - lo * n) / span
+            assert abs(direct - from_counts) <= 1e-12 * max(1.0, abs(direct)) * max(1, n) ** 0.5, (cls, direct, from_counts)
